@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/s of the fused quadcopter env step on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--workload c4|c2|k1] [--impl reference]
+
+One bench "step" = ONE launch of the fused kernel: `fuse` consecutive env steps over the rank's
+shard of envs, state in registers, the full rollout record (next obs, action, reward, done)
+written to HBM.  `value` = env-steps/s over all ranks with inputs resident in HBM; `e2e` = the
+same metric through the reference-facing API (DroneVecEnv.step with HOST numpy buffers: H2D of
+the actions and D2H of obs / reward / done inside the timed region).
+
+Workloads (BASELINE.json configs):
+  c4 (default)  configs[3] per-GPU shard: 8,388,608 envs per GPU (= 64M over 8 GPUs, weak
+                scaling), DroneGymEnv spec (15-dim obs, curriculum target, auto-reset),
+                in-kernel Philox random actions, fuse=32.
+  c2            configs[1]: 4096 envs x 1000 steps, random actions streamed from HBM, one launch.
+  k1            the SB3-style boundary: one env step per launch (dronecu_step), 8M envs.
+
+--impl reference times the reference's CPU implementation of the same path (the numpy port in
+oracle/ -- /root/reference is Python and cannot travel to the GPU box) on all host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+OBS_DIM = 15
+REC_BYTES = OBS_DIM * 4 + 16 + 4 + 1          # next_obs + action + reward + done per env-step
+STATE_BYTES = 80                              # 5 quads per env, read once + written once per launch
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (pynvml) -- runs during the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.ok = [], set(), False
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # pragma: no cover
+            self.err = repr(e)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def __enter__(self):
+        if self.ok:
+            self.t = threading.Thread(target=self._run, daemon=True)
+            self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self.ok:
+            self.t.join()
+
+    def summary(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": float(self.max),
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline: the numpy port of the reference env (oracle/) on the host cores
+# ------------------------------------------------------------------------------------------------
+_W = {}
+
+
+def _cpu_worker_init(n_envs, seed):
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    from oracle import drone_oracle as do
+    np.seterr(all="ignore")
+    _W["env"] = do.BatchedDroneOracle(n_envs, do.SINGLE, seed=seed, env_offset=seed * n_envs)
+    _W["rng"] = np.random.default_rng(seed)
+    _W["env"].reset()
+
+
+def _cpu_worker_steps(k_inner):
+    env, rng = _W["env"], _W["rng"]
+    for _ in range(k_inner):
+        a = rng.uniform(0, 7.3575, (env.n, 4)).astype(np.float32)
+        env.step(a)
+    return env.n * k_inner
+
+
+class CpuBaseline:
+    """`cores` worker processes, each stepping its own shard of the reference env port."""
+
+    def __init__(self, cores, envs_per_core=16384):
+        import multiprocessing as mp
+        self.cores, self.envs_per_core = cores, envs_per_core
+        ctx = mp.get_context("spawn")
+        self.pools = [ctx.Pool(1, initializer=_cpu_worker_init, initargs=(envs_per_core, i)) for i in range(cores)]
+
+    def step(self, k_inner):
+        res = [p.apply_async(_cpu_worker_steps, (k_inner,)) for p in self.pools]
+        return sum(r.get() for r in res)
+
+    def close(self):
+        for p in self.pools:
+            p.terminate()
+
+
+def time_cpu_baseline(cores, budget_s=12.0, k_inner=8):
+    cb = CpuBaseline(cores)
+    cb.step(2)                                   # warm-up (imports, first-touch)
+    t0, units = time.perf_counter(), 0
+    while True:
+        units += cb.step(k_inner)
+        dt = time.perf_counter() - t0
+        if dt > budget_s:
+            break
+    cb.close()
+    return units / dt, f"{cores} procs x {cb.envs_per_core} envs, DroneGymEnv spec + auto-reset, random actions, {units} env-steps in {dt:.1f}s"
+
+
+def run_reference(args):
+    """Reference arm: the reference's CPU path (numpy port, all host cores) on the same metric."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    k_inner = 8
+    cb = CpuBaseline(cores)
+    for _ in range(max(1, args.warmup)):
+        cb.step(k_inner)
+    t0, units = time.perf_counter(), 0
+    for _ in range(args.steps):
+        units += cb.step(k_inner)
+    dt = time.perf_counter() - t0
+    cb.close()
+    v = units / dt
+    sample = f"{cores} procs x {cb.envs_per_core} envs x {k_inner} env-steps per bench step"
+    line = {"impl": "reference", "metric": "env_steps_per_sec", "value": v, "unit": "env-steps/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD_NAMES[args.workload], "sample": sample},
+            "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+WORKLOAD_NAMES = {
+    "c4": "configs[3] shard: step-only fused rollout, 8388608 envs/GPU (64M over 8), DroneGymEnv spec, Philox actions",
+    "c2": "configs[1]: vectorized step-only, 4096 envs x 1000 steps, random actions streamed from HBM",
+    "k1": "SB3 boundary: one env step per launch (dronecu_step), 8388608 envs/GPU, streamed actions",
+}
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device and no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import drone_rl_b200 as drl
+
+    wl = args.workload
+    if wl == "c2":
+        n, fuse = 4096, 1000
+        cfg = drl.EnvConfig.vector()
+    else:
+        n, fuse = args.envs_per_gpu, (1 if wl == "k1" else args.fuse)
+        cfg = drl.EnvConfig.single()
+    D = cfg.obs_dim
+    batch = drl.DroneBatch(n, cfg, device=local, seed=args.seed, env_offset=rank * n)
+
+    # ---- device-resident buffers ----------------------------------------------------------------
+    nxt = torch.empty(fuse, n, D, device=dev)
+    rew = torch.empty(fuse, n, device=dev)
+    done = torch.empty(fuse, n, dtype=torch.uint8, device=dev)
+    if wl == "c4":
+        acts_in, acts_out = None, torch.empty(fuse, n, 4, device=dev)
+    else:
+        acts_in = torch.rand(fuse, n, 4, device=dev) * 7.3575
+        acts_out = None
+
+    def one_step():
+        if wl == "k1":
+            batch.step(acts_in[0], out={"obs": nxt[0], "reward": rew[0], "done": done[0]})
+        else:
+            batch.rollout(fuse, acts_in, next_obs=nxt, out_actions=acts_out, reward=rew, done=done)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        one_step()
+    barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    l0 = batch.launch_count
+    with ClockSampler(local) as clocks:
+        ev[0].record()
+        for i in range(args.steps):
+            one_step()
+            ev[i + 1].record()
+        barrier()
+    launches = batch.launch_count - l0
+    per = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]        # ms, per launch, on the launching stream
+    total_ms = ev[0].elapsed_time(ev[-1])
+    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    units = n * fuse * args.steps * world
+    value = units / (total_ms * 1e-3)
+
+    # ---- roofline of the dominant (only) kernel ----------------------------------------------------
+    in_bytes = 16 if acts_in is not None else 0
+    out_bytes = D * 4 + 4 + 1 + (16 if acts_out is not None else 0)
+    alg_bytes_per_launch = n * (fuse * (in_bytes + out_bytes) + 2 * STATE_BYTES)
+    avg_ms = float(np.mean(per))
+    peak, peak_src = peaks()
+    achieved = alg_bytes_per_launch / (avg_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "kernel": "rollout_kernel",
+                "algorithmic_bytes_per_env_step": in_bytes + out_bytes + 2 * STATE_BYTES / fuse,
+                "avg_launch_ms": avg_ms, "min_launch_ms": float(np.min(per))}
+    prof = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.isfile(prof):
+        try:
+            roofline["traffic"] = json.load(open(prof)).get(wl)
+        except Exception:
+            pass
+
+    # ---- e2e through the reference-facing API with HOST buffers ---------------------------------------
+    del nxt, rew, done, acts_in, acts_out
+    torch.cuda.empty_cache()
+    e2e = measure_e2e(drl, args, wl, n, rank, local, world, dist, barrier)
+    batch.close()
+
+    if rank == 0:
+        line = {"metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": WORKLOAD_NAMES[wl], "envs_per_gpu": n, "env_steps_per_launch": fuse,
+                           "obs_dim": D, "outputs": "next_obs+action+reward+done" if wl == "c4" else "next_obs+reward+done",
+                           "l2": "inputs larger than L2 (state %.0f MB, outputs %.1f GB per launch)" % (
+                               n * STATE_BYTES / 1e6, n * fuse * out_bytes / 1e9) if wl != "c2" else
+                           "L2 flushed by the 196 MB obs output of every launch"},
+                "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks.summary()}
+        if world == 1 and not args.no_cpu:
+            cores = os.cpu_count() or 1
+            v, sample = time_cpu_baseline(cores)
+            line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def measure_e2e(drl, args, wl, n, rank, local, world, dist, barrier):
+    """DroneVecEnv.step (SB3 VecEnv surface) with pinned host numpy buffers; every call copies the
+    actions H2D and obs / reward / done D2H."""
+    import torch
+    cfg = drl.EnvConfig.vector() if wl == "c2" else drl.EnvConfig.single()
+    env = drl.DroneVecEnv(n, seed=args.seed, device=local, env_offset=rank * n, info_mode="arrays", copy=False, config=cfg)
+    D = cfg.obs_dim
+    acts = torch.empty(n, 4, pin_memory=True).uniform_(0, 7.3575).numpy()
+    env.reset()
+    steps = max(3, min(args.steps, 10)) if wl != "c2" else 200
+    for _ in range(3):
+        env.step(acts)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        obs, rew, done, _ = env.step(acts)
+    barrier()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], device=torch.device("cuda", local), dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+    checksum = float(rew[: min(n, 1024)].sum())
+    env.close()
+    return {"value": n * steps * world / dt, "unit": "env-steps/s", "h2d_bytes_per_step": n * 16,
+            "d2h_bytes_per_step": n * (D * 4 + 4 + 1 + 1), "api": "DroneVecEnv.step (numpy, pinned)", "calls": steps,
+            "ms_per_call": 1e3 * dt / steps, "reward_checksum": checksum}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c4", choices=list(WORKLOAD_NAMES))
+    ap.add_argument("--envs-per-gpu", type=int, default=8_388_608)
+    ap.add_argument("--fuse", type=int, default=32)
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,238 @@
+// Fused K-step environment kernel and the small state-management kernels.
+//
+// Thread mapping: one env per thread, 256 envs per CTA, the state of an env lives in the
+// registers of its thread for all K steps of a launch (HBM sees the state once in, once out).
+// Observations ([n,D] row-major, what the reference's _get_obs returns: drone.py:77-79) are
+// transposed through a per-warp shared-memory tile (stride D = 15 or 12 words: odd / 4-bank
+// patterns, conflict-free for 15) and leave the SM as one bulk async copy per warp per step
+// (cp.async.bulk shared -> global, 32*D*4 contiguous bytes) instead of D strided 4-byte
+// stores per thread.
+#pragma once
+#include "env_core.cuh"
+
+namespace dronecu {
+
+constexpr int kBlock = 256;
+constexpr int kWarps = kBlock / 32;
+constexpr int kStatSlots = 128;   // episode statistics are spread over this many L2 lines
+
+struct StatSlot {   // one 64-byte line per slot
+  unsigned long long episodes, terminated, length_sum;
+  double return_sum;
+  unsigned long long pad[4];
+};
+
+struct RolloutArgs {
+  StatePlanes state;
+  EnvParams P;
+  int64_t n;
+  int32_t K;
+  uint64_t t0;                 // global step index of the first step of this launch (Philox index)
+  const float4* actions;       // [K,n] quads (STREAMED)
+  float* obs0;                 // [n,D]
+  float* next_obs;             // [K,n,D]
+  float4* out_actions;         // [K,n]
+  float* reward;               // [K,n]
+  uint8_t* done;               // [K,n]
+  uint8_t* truncated;          // [K,n]
+  float* terminal_obs;         // [K,n,D]  written only where done
+  float* episode_r;            // [K,n]    written only where done
+  int32_t* episode_l;          // [K,n]    written only where done
+  StatSlot* stats;             // [kStatSlots]
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+// One warp's 32 observations: registers -> smem tile -> global (bulk async copy when the
+// destination is 16-byte aligned and the warp is full, coalesced scalar stores otherwise).
+template <int OBS_DIM>
+__device__ __forceinline__ void emit_obs_rows(float* tile, float* gdst, const EnvState& s, int lane,
+                                              int valid, bool active) {
+  constexpr uint32_t kBytes = 32 * OBS_DIM * sizeof(float);
+  // the previous bulk copy must have finished READING the tile before it is overwritten
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  __syncwarp();
+  if (active) write_obs<OBS_DIM>(tile + lane * OBS_DIM, s);
+  const bool bulk = (valid == 32) && ((reinterpret_cast<uintptr_t>(gdst) & 15) == 0);
+  if (bulk) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy
+    __syncwarp();
+    if (lane == 0) {
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                   :: "l"(gdst), "r"(smem_u32(tile)), "r"(kBytes) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  } else {
+    __syncwarp();
+    for (int j = lane; j < valid * OBS_DIM; j += 32) gdst[j] = tile[j];
+    __syncwarp();
+  }
+}
+
+template <int OBS_DIM, bool RANDOMIZED, bool AUTORESET, int ACT_MODE>
+__global__ void __launch_bounds__(kBlock) rollout_kernel(const __grid_constant__ RolloutArgs A) {
+  __shared__ __align__(128) float tiles[kWarps][32 * OBS_DIM];
+  __shared__ unsigned long long blk_stats[3];
+  __shared__ double blk_ret;
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t warp_base = (int64_t)blockIdx.x * kBlock + warp * 32;
+  const int64_t i = warp_base + lane;
+  const bool active = i < A.n;
+  const int valid = (int)max((int64_t)0, min((int64_t)32, A.n - warp_base));
+  float* tile = tiles[warp];
+  const EnvParams& P = A.P;
+  const uint64_t env_id = P.env_offset + (uint64_t)i;
+
+  if (threadIdx.x < 3) blk_stats[threadIdx.x] = 0;
+  if (threadIdx.x == 3) blk_ret = 0.0;
+
+  EnvState s = {};
+  if (active) s = load_state(A.state, i);
+
+  if (A.obs0 != nullptr && valid > 0)
+    emit_obs_rows<OBS_DIM>(tile, A.obs0 + warp_base * OBS_DIM, s, lane, valid, active);
+
+  uint32_t n_done = 0, n_term = 0, len_sum = 0;
+  float ret_sum = 0.f;
+
+  float4 act = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (ACT_MODE == 0 && active) act = ld_quad_nc(A.actions + i);
+
+  for (int k = 0; k < A.K; ++k) {
+    const int64_t row = (int64_t)k * A.n;
+    float4 f = act;
+    if constexpr (ACT_MODE == 0) {
+      // software prefetch of the next step's action quad
+      if (active && k + 1 < A.K) act = ld_quad_nc(A.actions + row + A.n + i);
+    } else {
+      const uint4 w = env_stream(P.seed, env_id, A.t0 + (uint64_t)k, STREAM_ACTION);
+      f = make_float4(u01(w.x) * P.motor_max, u01(w.y) * P.motor_max, u01(w.z) * P.motor_max,
+                      u01(w.w) * P.motor_max);
+    }
+    const StepResult r = step_env(s, P, f);
+    const bool done = r.crashed || r.timeout;
+
+    if (active) {
+      if (A.out_actions != nullptr) st_quad(A.out_actions + row + i, f);
+      if (A.reward != nullptr) A.reward[row + i] = r.reward;
+      if (A.done != nullptr) A.done[row + i] = done ? 1 : 0;
+      if (A.truncated != nullptr) A.truncated[row + i] = (r.timeout && !r.crashed) ? 1 : 0;
+      if (done) {
+        n_done += 1;
+        n_term += r.crashed ? 1 : 0;
+        len_sum += (uint32_t)s.ep_len;
+        ret_sum += s.ep_ret;
+        if (A.terminal_obs != nullptr) write_obs<OBS_DIM>(A.terminal_obs + (row + i) * OBS_DIM, s);
+        if (A.episode_r != nullptr) A.episode_r[row + i] = s.ep_ret;
+        if (A.episode_l != nullptr) A.episode_l[row + i] = s.ep_len;
+        if constexpr (AUTORESET) {
+          reset_env<RANDOMIZED>(s, P, env_id);
+        } else {
+          s.ep_ret = 0.f;   // VecMonitor zeroes its accumulators on done even without a reset
+          s.ep_len = 0;
+        }
+      }
+    }
+    if (A.next_obs != nullptr && valid > 0)
+      emit_obs_rows<OBS_DIM>(tile, A.next_obs + (row + warp_base) * OBS_DIM, s, lane, valid, active);
+  }
+
+  if (active) store_state(A.state, i, s);
+
+  // episode statistics: warp shuffle -> block smem -> one atomic set per CTA into a hashed slot
+  __syncthreads();   // blk_stats initialised
+  if (__ballot_sync(0xffffffffu, n_done != 0)) {
+    n_done = __reduce_add_sync(0xffffffffu, n_done);
+    n_term = __reduce_add_sync(0xffffffffu, n_term);
+    len_sum = __reduce_add_sync(0xffffffffu, len_sum);
+    double rs = (double)ret_sum;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, o);
+    if (lane == 0) {
+      atomicAdd(&blk_stats[0], (unsigned long long)n_done);
+      atomicAdd(&blk_stats[1], (unsigned long long)n_term);
+      atomicAdd(&blk_stats[2], (unsigned long long)len_sum);
+      atomicAdd(&blk_ret, rs);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && blk_stats[0] != 0) {
+    StatSlot* slot = A.stats + (blockIdx.x % kStatSlots);
+    atomicAdd(&slot->episodes, blk_stats[0]);
+    atomicAdd(&slot->terminated, blk_stats[1]);
+    atomicAdd(&slot->length_sum, blk_stats[2]);
+    atomicAdd(&slot->return_sum, blk_ret);
+  }
+  // the shared tile must stay alive until the bulk engine has read it
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// reset (masked) + observation of every row.  drone.py:48-75 / vectorized_drone.py:38-57
+// ---------------------------------------------------------------------------------------------
+template <int OBS_DIM, bool RANDOMIZED>
+__global__ void __launch_bounds__(kBlock) reset_kernel(StatePlanes sp, const __grid_constant__ EnvParams P,
+                                                       int64_t n, const uint8_t* mask, float* obs,
+                                                       int zero_first) {
+  __shared__ __align__(128) float tiles[kWarps][32 * OBS_DIM];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t warp_base = (int64_t)blockIdx.x * kBlock + warp * 32;
+  const int64_t i = warp_base + lane;
+  const bool active = i < n;
+  const int valid = (int)max((int64_t)0, min((int64_t)32, n - warp_base));
+  EnvState s = {};
+  if (active) {
+    if (!zero_first) s = load_state(sp, i);   // zero_first: the constructor's reset (ep_num 0 -> 1)
+    if (zero_first || mask == nullptr || mask[i] != 0) {
+      reset_env<RANDOMIZED>(s, P, P.env_offset + (uint64_t)i);
+      store_state(sp, i, s);
+    }
+  }
+  if (obs != nullptr && valid > 0)
+    emit_obs_rows<OBS_DIM>(tiles[warp], obs + warp_base * OBS_DIM, s, lane, valid, active);
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// SoA views for attribute access / teacher-forced tests (cold path)
+// ---------------------------------------------------------------------------------------------
+struct StateView {
+  float *pos, *vel, *euler, *omega, *target, *ep_ret;
+  int32_t *step, *ep_num, *ep_len;
+};
+
+__global__ void get_state_kernel(StatePlanes sp, int64_t n, StateView v) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const EnvState s = load_state(sp, i);
+  if (v.pos) { v.pos[3 * i] = s.px; v.pos[3 * i + 1] = s.py; v.pos[3 * i + 2] = s.pz; }
+  if (v.vel) { v.vel[3 * i] = s.vx; v.vel[3 * i + 1] = s.vy; v.vel[3 * i + 2] = s.vz; }
+  if (v.euler) { v.euler[3 * i] = s.roll; v.euler[3 * i + 1] = s.pitch; v.euler[3 * i + 2] = s.yaw; }
+  if (v.omega) { v.omega[3 * i] = s.wp; v.omega[3 * i + 1] = s.wq; v.omega[3 * i + 2] = s.wr; }
+  if (v.target) { v.target[3 * i] = s.tx; v.target[3 * i + 1] = s.ty; v.target[3 * i + 2] = s.tz; }
+  if (v.step) v.step[i] = s.step;
+  if (v.ep_num) v.ep_num[i] = s.ep_num;
+  if (v.ep_len) v.ep_len[i] = s.ep_len;
+  if (v.ep_ret) v.ep_ret[i] = s.ep_ret;
+}
+
+__global__ void set_state_kernel(StatePlanes sp, int64_t n, StateView v) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  EnvState s = load_state(sp, i);
+  if (v.pos) { s.px = v.pos[3 * i]; s.py = v.pos[3 * i + 1]; s.pz = v.pos[3 * i + 2]; }
+  if (v.vel) { s.vx = v.vel[3 * i]; s.vy = v.vel[3 * i + 1]; s.vz = v.vel[3 * i + 2]; }
+  if (v.euler) { s.roll = v.euler[3 * i]; s.pitch = v.euler[3 * i + 1]; s.yaw = v.euler[3 * i + 2]; }
+  if (v.omega) { s.wp = v.omega[3 * i]; s.wq = v.omega[3 * i + 1]; s.wr = v.omega[3 * i + 2]; }
+  if (v.target) { s.tx = v.target[3 * i]; s.ty = v.target[3 * i + 1]; s.tz = v.target[3 * i + 2]; }
+  if (v.step) s.step = v.step[i];
+  if (v.ep_num) s.ep_num = v.ep_num[i];
+  if (v.ep_len) s.ep_len = v.ep_len[i];
+  if (v.ep_ret) s.ep_ret = v.ep_ret[i];
+  store_state(sp, i, s);
+}
+
+}  // namespace dronecu

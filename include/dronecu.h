@@ -1,0 +1,182 @@
+/*
+ * dronecu.h -- C ABI of libdronecu.so, the B200 (sm_100a) batched quadcopter environment.
+ *
+ * The reference (henryplas/drone_rl) has no FFI of its own: its boundary is the Python
+ * object protocol that Stable-Baselines3 and its scripts call.  Each
+ * entry point below names the reference interface it stands in for; the Python classes in
+ * drone_rl_b200/ (same names and argument meaning as the reference's) bind to these with
+ * ctypes -- see INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; "d_" pointers are CUDA device pointers on the handle's
+ *     device, "h_" pointers are host pointers.  `stream` is a cudaStream_t passed as void*
+ *     (NULL = the legacy default stream).
+ *   - every function returns 0 (DRONECU_OK) or a negative dronecu_status; a text for the
+ *     last error on the calling thread is available from dronecu_last_error().
+ *   - a handle is bound to one device; calls on one handle must be serialised by the caller
+ *     (the reference env is single-threaded and not re-entrant either); different handles
+ *     are independent.
+ *   - there is NO CPU fallback: without a CUDA device dronecu_create fails with
+ *     DRONECU_ERR_CUDA.
+ */
+#ifndef DRONECU_H
+#define DRONECU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DRONECU_VERSION 100
+
+typedef enum {
+  DRONECU_OK = 0,
+  DRONECU_ERR_INVALID = -1, /* bad argument */
+  DRONECU_ERR_CUDA = -2,    /* CUDA runtime error (text in dronecu_last_error) */
+  DRONECU_ERR_ALLOC = -3,
+  DRONECU_ERR_UNSUPPORTED = -4
+} dronecu_status;
+
+/* dronecu_config.flags */
+#define DRONECU_RANDOMIZED 1u /* random start + curriculum target  (DroneEnv.reset, drone.py:48-75)   */
+#define DRONECU_AUTORESET 2u  /* SB3 DummyVecEnv semantics: reset a done env inside step (train.py:18-20) */
+
+/* Every literal of the reference lives here so nothing is hard-coded in the kernels.
+ * drone.py:14-46 (DroneEnv.__init__) / vectorized_drone.py:13-36 (VectorizedDroneEnv.__init__). */
+typedef struct dronecu_config {
+  double dt;                /* 0.02   drone.py:14,25                                */
+  double mass;              /* 1.0    drone.py:21                                   */
+  double gravity;           /* 9.81   drone.py:22                                   */
+  double inertia[3];        /* 0.005, 0.005, 0.01   drone.py:24                     */
+  double arm_length;        /* 0.5    drone.py:36                                   */
+  double k_yaw;             /* 0.01   drone.py:40                                   */
+  double reward_scale;      /* 0.01   drone.py:142 / vectorized_drone.py:205        */
+  double bonus_radius;      /* 0.05   drone.py:147   | 1.0  vectorized_drone.py:207 */
+  double bonus;             /* 1.0    drone.py:148                                  */
+  double z_floor;           /* 0.0    drone.py:154                                  */
+  double r_max;             /* 50.0   drone.py:154                                  */
+  double fixed_target[3];   /* 0,0,10 vectorized_drone.py:30 (when !RANDOMIZED)     */
+  double fixed_start[3];    /* .1,.1,.1 vectorized_drone.py:50 (when !RANDOMIZED)   */
+  double start_z;           /* 1.0    drone.py:57                                   */
+  double target_z;          /* 1.0 + add(=0)   drone.py:30,73                       */
+  double curriculum_step;   /* 0.1    drone.py:70                                   */
+  int32_t curriculum_period;/* 2000   drone.py:68                                   */
+  int32_t max_steps;        /* 200    drone.py:43    | 1000 vectorized_drone.py:33  */
+  int32_t obs_dim;          /* 15     drone.py:79    | 12   vectorized_drone.py:61  */
+  uint32_t flags;           /* DRONECU_RANDOMIZED | DRONECU_AUTORESET               */
+} dronecu_config;
+
+typedef struct dronecu_env dronecu_env;
+
+/* Where the K-step kernel takes its motor forces from. */
+typedef enum {
+  DRONECU_ACTIONS_STREAMED = 0, /* d_actions[K,n,4] float32, used as given (the env never clips: drone.py:103) */
+  DRONECU_ACTIONS_UNIFORM = 1   /* in-kernel Philox U[0, motor_max) -- the "random actions" workload        */
+} dronecu_action_mode;
+
+/* Optional outputs of dronecu_rollout; any pointer may be NULL (that output is not written). */
+typedef struct dronecu_rollout_out {
+  float* d_obs0;        /* [n,D]    observation before the first step                              */
+  float* d_next_obs;    /* [K,n,D]  observation returned by step k (post auto-reset, as VecEnv.step) */
+  float* d_actions;     /* [K,n,4]  action applied at step k (useful with ACTIONS_UNIFORM)          */
+  float* d_reward;      /* [K,n]    float32 reward (SB3's DummyVecEnv stores float32)               */
+  uint8_t* d_done;      /* [K,n]    crash | out-of-range | time limit (drone.py:154-157)            */
+  uint8_t* d_truncated; /* [K,n]    time limit only (Gymnasium's `truncated`)                       */
+} dronecu_rollout_out;
+
+/* Outputs of dronecu_step / dronecu_step_host (device resp. host pointers); d_obs, d_reward and
+ * d_done are what VecEnv.step_wait returns, the rest is what SB3 puts into `infos`.  Any pointer
+ * may be NULL.  The three "where done" arrays are only written in rows whose done flag is set. */
+typedef struct dronecu_step_out {
+  float* d_obs;          /* [n,D]  next observation (after the auto-reset, if any)              */
+  float* d_reward;       /* [n]    float32                                                      */
+  uint8_t* d_done;       /* [n]                                                                 */
+  uint8_t* d_truncated;  /* [n]    time limit only                                              */
+  float* d_terminal_obs; /* [n,D]  where done: pre-reset observation (info["terminal_observation"]) */
+  float* d_episode_r;    /* [n]    where done: VecMonitor episode return (info["episode"]["r"])  */
+  int32_t* d_episode_l;  /* [n]    where done: VecMonitor episode length (info["episode"]["l"])  */
+} dronecu_step_out;
+
+/* SoA view used by get/set state; any pointer may be NULL.  All device pointers. */
+typedef struct dronecu_state_view {
+  float* d_pos;     /* [n,3]  DroneEnv.pos    drone.py:57  */
+  float* d_vel;     /* [n,3]  DroneEnv.vel    drone.py:58  */
+  float* d_euler;   /* [n,3]  DroneEnv.euler  drone.py:59  */
+  float* d_omega;   /* [n,3]  DroneEnv.omega  drone.py:60  */
+  float* d_target;  /* [n,3]  DroneEnv.target drone.py:73  */
+  int32_t* d_step;  /* [n]    DroneEnv.current_step drone.py:66 */
+  int32_t* d_ep_num;/* [n]    DroneEnv.ep_num drone.py:61  */
+  int32_t* d_ep_len;/* [n]    VecMonitor episode length    */
+  float* d_ep_ret;  /* [n]    VecMonitor episode return    */
+} dronecu_state_view;
+
+/* Episode statistics accumulated on the device since the last reset of the counters
+ * (what SB3's VecMonitor feeds `rollout/ep_rew_mean`, `rollout/ep_len_mean`). */
+typedef struct dronecu_stats {
+  uint64_t episodes;   /* finished episodes                            */
+  uint64_t terminated; /* of which ended by crash / out of range       */
+  uint64_t truncated;  /* of which ended by the time limit only        */
+  uint64_t length_sum; /* sum of episode lengths                       */
+  double return_sum;   /* sum of episode returns (float32 accumulated) */
+  uint64_t env_steps;  /* env-steps executed                           */
+} dronecu_stats;
+
+int dronecu_version(void);
+const char* dronecu_last_error(void);
+
+/* Reference defaults: DroneEnv/DroneGymEnv (drone.py:14-46, :254-264) wrapped the way
+ * train.py:18-20 wraps it (auto-reset), and VectorizedDroneEnv (vectorized_drone.py:13-36). */
+void dronecu_config_single(dronecu_config* cfg);
+void dronecu_config_vector(dronecu_config* cfg);
+
+/* DroneGymEnv() x n_envs / VectorizedDroneGymEnv(batch_size=n_envs): allocates the state on
+ * `device` and performs the constructor's reset (drone.py:46, vectorized_drone.py:36), so a
+ * fresh env has ep_num == 1.  Env i has global id env_offset + i; all randomness is keyed by
+ * (seed, global id), so results do not depend on how envs are sharded over GPUs. */
+int dronecu_create(const dronecu_config* cfg, int device, int64_t n_envs, int64_t env_offset,
+                   uint64_t seed, dronecu_env** out);
+int dronecu_destroy(dronecu_env* env);
+
+int64_t dronecu_num_envs(const dronecu_env* env);
+int dronecu_obs_dim(const dronecu_env* env);
+int64_t dronecu_global_step(const dronecu_env* env); /* steps taken since create (Philox index) */
+double dronecu_motor_max(const dronecu_env* env);    /* 3*m*g/4, drone.py:263 */
+
+/* DroneGymEnv.reset (drone.py:270-271, :48-75) / VectorizedDroneGymEnv.reset
+ * (vectorized_drone.py:265-266, :38-57).  d_mask [n] (NULL = every env): rows with a
+ * non-zero byte are reset.  d_obs [n,D] (nullable) receives the observation of ALL rows. */
+int dronecu_reset(dronecu_env* env, const uint8_t* d_mask, float* d_obs, void* stream);
+
+/* DroneGymEnv.step (drone.py:266-268, :81-159) under DummyVecEnv.step_wait + VecMonitor, or
+ * VectorizedDroneGymEnv.step (vectorized_drone.py:262-263, :135-216).  d_actions [n,4] float32,
+ * 16-byte aligned, used as given (no clipping, no validation -- like the reference). */
+int dronecu_step(dronecu_env* env, const float* d_actions, const dronecu_step_out* out, void* stream);
+
+/* K consecutive steps in ONE launch; the state stays in registers between steps.  Equivalent
+ * to K calls of dronecu_step (bit-identical results). */
+int dronecu_rollout(dronecu_env* env, int K, int action_mode, const float* d_actions,
+                    const dronecu_rollout_out* out, void* stream);
+
+/* Same as dronecu_step but with HOST buffers (numpy arrays): the H2D copy of the actions,
+ * the kernel and the D2H copies of obs / reward / done all happen inside the call, through
+ * pinned staging buffers owned by the handle.  This is what DroneVecEnv.step_wait uses. */
+int dronecu_step_host(dronecu_env* env, const float* h_actions, const dronecu_step_out* host_out);
+int dronecu_reset_host(dronecu_env* env, const uint8_t* h_mask, float* h_obs);
+
+/* Attribute access (`env.pos`, `get_attr('pos')`: traj_tb.py:34) and teacher-forced tests. */
+int dronecu_get_state(dronecu_env* env, const dronecu_state_view* view, void* stream);
+int dronecu_set_state(dronecu_env* env, const dronecu_state_view* view, void* stream);
+int dronecu_get_state_host(dronecu_env* env, const dronecu_state_view* host_view);
+int dronecu_set_state_host(dronecu_env* env, const dronecu_state_view* host_view);
+
+/* VecMonitor totals.  Synchronises the handle's work first.  reset != 0 zeroes the counters. */
+int dronecu_episode_stats(dronecu_env* env, dronecu_stats* h_out, int reset);
+
+/* Number of kernel launches this handle has issued (bench.py's gpu_launches). */
+uint64_t dronecu_launch_count(const dronecu_env* env);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DRONECU_H */
