@@ -1,0 +1,91 @@
+"""TEST INFRASTRUCTURE: check a recorded rollout transition-by-transition against the oracle.
+
+Open-loop float32 and float64 trajectories of this system separate exponentially under random
+motor forces (the reference against itself drifts 0.2 rad in 26 steps when only the
+action dtype changes), so a K-step record is verified *teacher-forced from its own rows*: the
+float64 oracle is restarted from the recorded float32 observation of step k-1 and must reproduce
+the recorded observation / reward / done of step k within the per-step tolerance.  Rows that were
+auto-reset are checked bit-exactly against the Philox-fed reset (drone.py:48-75).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import drone_oracle as do
+from . import philox
+
+TOL_REL = 1e-5
+
+
+def check_rollout(obs0, actions, next_obs, reward, done, *, spec=do.SINGLE, seed=0, env_ids=None,
+                  ep_num0=None, step0=None, tol=TOL_REL, sing_cos=1e-3):
+    """obs0 [n,D]; actions [K,n,4]; next_obs [K,n,D]; reward [K,n]; done [K,n] (bool).
+
+    ep_num0 / step0: episode number (default 2: constructor reset + reset()) and step counter
+    (default 0) of every env before the first step.
+    Returns a dict with the worst error/bound ratio and the counts of borderline decisions.
+    Raises AssertionError on a violation.
+    """
+    K, n = actions.shape[:2]
+    D = spec.obs_dim
+    env_ids = np.arange(n, dtype=np.uint64) if env_ids is None else np.asarray(env_ids, dtype=np.uint64)
+    ep_num = np.broadcast_to(np.asarray(2 if ep_num0 is None else ep_num0, dtype=np.int64), (n,)).copy()
+    step = np.zeros(n, dtype=np.int64) if step0 is None else np.broadcast_to(np.asarray(step0, dtype=np.int64), (n,)).copy()
+    prev = np.asarray(obs0, dtype=np.float32)
+    worst, borderline, n_done, n_sing = 0.0, 0, 0, 0
+    with np.errstate(all="ignore"):
+        for k in range(K):
+            p64 = prev.astype(np.float64)
+            pos, vel, eul, om = p64[:, 0:3], p64[:, 3:6], p64[:, 6:9], p64[:, 9:12]
+            target = (p64[:, 12:15] + pos) if D == 15 else np.tile(np.array([0.0, 0.0, 10.0]), (n, 1))
+            npos, nvel, neul, nom = do.dynamics_step(pos, vel, eul, om, actions[k].astype(np.float64))
+            rew, crashed = do.reward_and_crash(npos, target, spec.bonus_radius)
+            step += 1
+            timeout = step >= spec.max_steps
+            d_ref = crashed | timeout
+            d_got = np.asarray(done[k]).astype(bool)
+            rad = np.linalg.norm(npos, axis=1)
+            margin = ((np.abs(npos[:, 2]) > 1e-5) & (np.abs(rad - 50.0) > 1e-4)) | ~np.isfinite(rad)
+            assert np.array_equal(d_got[margin], d_ref[margin]), f"done mismatch at step {k}"
+            borderline += int((~margin).sum())
+            live = (~d_got & ~d_ref) if spec.auto_reset else (d_got == d_ref)
+            ref_obs = do.build_obs(npos, nvel, neul, nom, target, D).astype(np.float64)
+            got_obs = np.asarray(next_obs[k], dtype=np.float64)
+            amp = np.ones((n, D))
+            cosp = np.cos(eul[:, 1])
+            sing = np.abs(cosp) < sing_cos
+            n_sing += int(sing.sum())
+            amp[sing, 6] = amp[sing, 8] = 1.0 / np.maximum(cosp[sing] ** 2, 1e-30)
+            # the recorded target-pos is float32(t - p): reconstructing t adds one float32 rounding
+            if D == 15:
+                amp[:, 12:15] = 2.0
+            fin = np.isfinite(ref_obs) & live[:, None]
+            assert np.array_equal(np.isnan(got_obs[live]), np.isnan(ref_obs[live])), f"NaN pattern, step {k}"
+            err = np.abs(got_obs - ref_obs)[fin]
+            bound = (tol * np.maximum(np.abs(ref_obs), 1.0) * amp)[fin]
+            if err.size:
+                ratio = float(np.max(err / bound))
+                worst = max(worst, ratio)
+                assert ratio <= 1.0, f"obs outside tolerance at step {k}: err/bound {ratio:.3g}"
+            both = d_got == d_ref
+            rfin = np.isfinite(rew) & both
+            rerr = np.abs(np.asarray(reward[k], dtype=np.float64) - rew)[rfin]
+            rbound = 2 * tol * np.maximum(np.abs(rew[rfin]), 1.0)
+            assert not (rerr > rbound).any(), f"reward outside tolerance at step {k}"
+            # auto-reset rows: bit-exact Philox-fed reset observation
+            rows = np.flatnonzero(d_got)
+            n_done += rows.size
+            if spec.auto_reset and rows.size:
+                ep_num[rows] += 1
+                step[rows] = 0
+                u = philox.reset_uniforms(seed, env_ids[rows], ep_num[rows])
+                eps = do.curriculum_eps(ep_num[rows])
+                rp = np.stack([u[0] - 0.5, u[1] - 0.5, np.ones(rows.size)], 1)
+                rt = np.stack([eps * u[2], eps * u[3], eps * u[4] + 1.0], 1)
+                # the CUDA env stores the target as float32, then forms target - pos in float32
+                rt32, rp32 = rt.astype(np.float32), rp.astype(np.float32)
+                ref_reset = np.concatenate([rp32, np.zeros((rows.size, 9), np.float32), rt32 - rp32], 1)
+                assert np.array_equal(np.asarray(next_obs[k])[rows], ref_reset[:, :D]), f"reset obs at step {k}"
+            prev = np.asarray(next_obs[k], dtype=np.float32)
+    return {"worst_err_over_bound": worst, "borderline_done": borderline, "dones": n_done,
+            "near_singular_rows": n_sing, "transitions": K * n}

@@ -391,3 +391,33 @@ def test_errors_are_loud(drl):
     with pytest.raises(drl.DronecuError):
         drl.DroneBatch(4, drl.EnvConfig.single(obs_dim=13))
     b.close()
+
+
+def test_full_size_rollout_properties(drl):
+    """BASELINE size (1M envs, the C3 batch): K-fusion invariance, shard invariance and episode
+    bookkeeping at full size, plus every transition of a strided 4k-env sample checked against the
+    float64 oracle teacher-forced from the record (oracle/verify.py)."""
+    from oracle import verify
+    n, K, seed = 1 << 20, 24, 5
+    b = drl.DroneBatch(n, drl.EnvConfig.single(), seed=seed)
+    obs0 = b.reset()
+    nxt = b.empty(K, n, 15); act = b.empty(K, n, 4); rew = b.empty(K, n); done = b.empty(K, n, dtype=torch.uint8)
+    b.rollout(K, None, next_obs=nxt, out_actions=act, reward=rew, done=done)
+    st = b.episode_stats()
+    assert st["episodes"] == int(done.sum().item()) and st["env_steps"] == n * K
+    assert 0.02 < done.float().mean().item() < 0.05            # ~1/32 under random actions (SURVEY section 6)
+    sel = torch.arange(0, n, 257, device="cuda")
+    rep = verify.check_rollout(obs0[sel].cpu().numpy(), act[:, sel].cpu().numpy(), nxt[:, sel].cpu().numpy(),
+                               rew[:, sel].cpu().numpy(), done[:, sel].cpu().numpy().astype(bool),
+                               spec=do.SINGLE, seed=seed, env_ids=sel.cpu().numpy())
+    assert rep["dones"] > 100 and rep["borderline_done"] <= 3
+    # same global ids from a second handle covering only the tail quarter, in two launches
+    q = n // 4
+    b2 = drl.DroneBatch(q, drl.EnvConfig.single(), seed=seed, env_offset=3 * q)
+    b2.reset()
+    nxt2 = b2.empty(K, q, 15)
+    b2.rollout(K // 2, None, next_obs=nxt2[: K // 2])
+    b2.rollout(K - K // 2, None, next_obs=nxt2[K // 2:])
+    assert torch.equal(nxt2, nxt[:, 3 * q:])
+    print("full-size:", rep)
+    b.close(); b2.close()
