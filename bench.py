@@ -276,7 +276,7 @@ def run_gpu(args):
     # ---- e2e through the reference-facing API with HOST buffers ---------------------------------------
     del nxt, rew, done, acts_in, acts_out
     torch.cuda.empty_cache()
-    e2e = measure_e2e(drl, args, wl, n, rank, local, world, dist, barrier)
+    e2e = None if args.no_e2e else measure_e2e(drl, args, wl, n, rank, local, world, dist, barrier)
     batch.close()
 
     if rank == 0:
@@ -339,6 +339,7 @@ def main():
     ap.add_argument("--fuse", type=int, default=32)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the e2e leg (A/B kernel timing only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

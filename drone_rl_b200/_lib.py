@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdronecu.so")
+LIB_PATH = os.environ.get("DRONECU_LIB", os.path.join(_HERE, "libdronecu.so"))   # DRONECU_LIB: A/B builds for profiling
 
 
 class DronecuError(RuntimeError):

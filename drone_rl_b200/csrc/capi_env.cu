@@ -94,16 +94,22 @@ static EnvParams digest(const dronecu_config& c, uint64_t seed, int64_t env_offs
   P.curriculum_step = c.curriculum_step;
   P.curriculum_period = c.curriculum_period;
   P.max_steps = c.max_steps;
+  P.inv_curriculum_period = (float)(1.0 / (double)c.curriculum_period);
+  P.r_max_sq = (float)(c.r_max * c.r_max);
   P.seed = seed;
   P.env_offset = (uint64_t)env_offset;
   return P;
 }
 
-static inline unsigned grid_for(int64_t n) { return (unsigned)((n + kBlock - 1) / kBlock); }
+// CTA size: 256 threads when there are enough envs to fill the 148 SMs several times over;
+// small batches (configs[1]: 4096 envs) use one warp per CTA so they spread over all SMs.
+static inline unsigned block_for(int64_t n) { return n >= (int64_t)148 * kBlock * 2 ? kBlock : (n >= 148 * 64 * 2 ? 64 : 32); }
+static inline unsigned grid_for(int64_t n, unsigned block = kBlock) { return (unsigned)((n + block - 1) / block); }
 
 template <int D, bool R>
 static void launch_reset_t(dronecu_env* e, const uint8_t* mask, float* obs, int zero_first, cudaStream_t st) {
-  reset_kernel<D, R><<<grid_for(e->n), kBlock, 0, st>>>(e->sp, e->P, e->n, mask, obs, zero_first);
+  const unsigned blk = block_for(e->n);
+  reset_kernel<D, R><<<grid_for(e->n, blk), blk, 0, st>>>(e->sp, e->P, e->n, mask, obs, zero_first);
 }
 
 static int launch_reset(dronecu_env* e, const uint8_t* mask, float* obs, int zero_first, cudaStream_t st) {
@@ -116,16 +122,24 @@ static int launch_reset(dronecu_env* e, const uint8_t* mask, float* obs, int zer
 }
 
 template <int D, bool R, bool AR>
-static void launch_rollout_t(const RolloutArgs& a, int mode, unsigned grid, cudaStream_t st) {
-  if (mode == DRONECU_ACTIONS_STREAMED) rollout_kernel<D, R, AR, 0><<<grid, kBlock, 0, st>>>(a);
-  else rollout_kernel<D, R, AR, 1><<<grid, kBlock, 0, st>>>(a);
+static void launch_rollout_t(const RolloutArgs& a, int mode, bool record, unsigned grid, unsigned blk, cudaStream_t st) {
+  if (mode == DRONECU_ACTIONS_STREAMED) {
+    if (record) rollout_kernel<D, R, AR, 0, true><<<grid, blk, 0, st>>>(a);
+    else rollout_kernel<D, R, AR, 0, false><<<grid, blk, 0, st>>>(a);
+  } else {
+    if (record) rollout_kernel<D, R, AR, 1, true><<<grid, blk, 0, st>>>(a);
+    else rollout_kernel<D, R, AR, 1, false><<<grid, blk, 0, st>>>(a);
+  }
 }
 
 static int launch_rollout(dronecu_env* e, const RolloutArgs& a, int mode, cudaStream_t st) {
   const bool R = e->cfg.flags & DRONECU_RANDOMIZED, AR = e->cfg.flags & DRONECU_AUTORESET;
-  const unsigned g = grid_for(e->n);
+  const unsigned blk = block_for(e->n), g = grid_for(e->n, blk);
   const int D = e->cfg.obs_dim;
-#define DISPATCH(DD, RR, AA) if (D == DD && R == RR && AR == AA) launch_rollout_t<DD, RR, AA>(a, mode, g, st);
+  // the "rollout record" specialisation: exactly next_obs + reward + done (+ the in-kernel action)
+  const bool record = a.next_obs && a.reward && a.done && !a.truncated && !a.terminal_obs && !a.episode_r &&
+                      !a.episode_l && ((mode == DRONECU_ACTIONS_UNIFORM) == (a.out_actions != nullptr));
+#define DISPATCH(DD, RR, AA) if (D == DD && R == RR && AR == AA) launch_rollout_t<DD, RR, AA>(a, mode, record, g, blk, st);
   DISPATCH(15, true, true) DISPATCH(15, true, false) DISPATCH(15, false, true) DISPATCH(15, false, false)
   DISPATCH(12, true, true) DISPATCH(12, true, false) DISPATCH(12, false, true) DISPATCH(12, false, false)
 #undef DISPATCH

@@ -27,6 +27,7 @@ struct EnvParams {
   float start_z, target_z, motor_max;
   double curriculum_step;
   int32_t curriculum_period, max_steps;
+  float inv_curriculum_period, r_max_sq;
   uint64_t seed, env_offset;
 };
 
@@ -98,20 +99,32 @@ __device__ __forceinline__ void reset_env(EnvState& s, const EnvParams& P, uint6
   s.ep_len = 0;
   s.ep_ret = 0.f;
   if constexpr (RANDOMIZED) {
-    // exactly five uniforms, in the reference's order pos.x pos.y tgt.x tgt.y tgt.z (drone.py:57,73)
-    const uint4 a = env_stream(P.seed, env_id, (uint64_t)(uint32_t)s.ep_num, STREAM_RESET_A);
-    const uint4 b = env_stream(P.seed, env_id, (uint64_t)(uint32_t)s.ep_num, STREAM_RESET_B);
-    s.px = u01(a.x) - 0.5f;   // exact: u is a multiple of 2^-24
-    s.py = u01(a.y) - 0.5f;
+    // exactly five uniforms, in the reference's order pos.x pos.y tgt.x tgt.y tgt.z (drone.py:57,73),
+    // out of ONE Philox call: 4 x 24 high bits + the 3 low bytes of words 0..2 (oracle/philox.py)
+    const uint4 w = env_stream(P.seed, env_id, (uint64_t)(uint32_t)s.ep_num, STREAM_RESET);
+    s.px = u01(w.x) - 0.5f;   // exact: u is a multiple of 2^-24
+    s.py = u01(w.y) - 0.5f;
     s.pz = P.start_z;
     // eps: the reference ACCUMULATES eps += 0.1 in float64 every curriculum_period episodes
     // (drone.py:68-70) -> 0.1, 0.2, 0.30000000000000004 ...; replay the accumulation.
-    double eps = 0.0;
-    const int bumps = s.ep_num / P.curriculum_period;
-    for (int k = 0; k < bumps; ++k) eps += P.curriculum_step;
-    s.tx = (float)(eps * (double)u01(a.z));
-    s.ty = (float)(eps * (double)u01(a.w));
-    s.tz = (float)(eps * (double)u01(b.x) + (double)P.target_z);
+    // bumps = ep_num / period without an integer division: float estimate, exact fix-up
+    // (|estimate - true| < 1 for every 31-bit ep_num)
+    int bumps = 0;
+    if (s.ep_num >= P.curriculum_period) {
+      bumps = __float2int_rd((float)s.ep_num * P.inv_curriculum_period);
+      const int r = s.ep_num - bumps * P.curriculum_period;
+      bumps += (r >= P.curriculum_period) ? 1 : ((r < 0) ? -1 : 0);
+    }
+    if (bumps == 0) {         // eps == 0: target = [0, 0, target_z] exactly
+      s.tx = 0.f; s.ty = 0.f; s.tz = P.target_z;
+    } else {
+      double eps = 0.0;
+      for (int k = 0; k < bumps; ++k) eps += P.curriculum_step;
+      const uint32_t lo = (w.x & 255u) | ((w.y & 255u) << 8) | ((w.z & 255u) << 16);
+      s.tx = (float)(eps * (double)u01(w.z));
+      s.ty = (float)(eps * (double)u01(w.w));
+      s.tz = (float)(eps * (double)((float)lo * 5.9604644775390625e-8f) + (double)P.target_z);
+    }
   } else {
     s.px = P.fixed_start[0]; s.py = P.fixed_start[1]; s.pz = P.fixed_start[2];
     s.tx = P.fixed_target[0]; s.ty = P.fixed_target[1]; s.tz = P.fixed_target[2];
@@ -169,8 +182,9 @@ __device__ __forceinline__ StepResult step_env(EnvState& s, const EnvParams& P, 
   StepResult r;
   r.reward = -P.reward_scale * dist;
   if (dist < P.bonus_radius) r.reward += P.bonus;
-  const float rad = sqrtf(s.px * s.px + s.py * s.py + s.pz * s.pz);
-  r.crashed = (s.pz < P.z_floor) || (rad > P.r_max);
+  // |pos| > r_max tested on the squares (sqrt is monotonic; NaN still compares false)
+  const float rad_sq = s.px * s.px + s.py * s.py + s.pz * s.pz;
+  r.crashed = (s.pz < P.z_floor) || (rad_sq > P.r_max_sq);
   s.step += 1;
   r.timeout = s.step >= P.max_steps;
   s.ep_ret += r.reward;   // VecMonitor

@@ -3,10 +3,9 @@
 // Thread mapping: one env per thread, 256 envs per CTA, the state of an env lives in the
 // registers of its thread for all K steps of a launch (HBM sees the state once in, once out).
 // Observations ([n,D] row-major, what the reference's _get_obs returns: drone.py:77-79) are
-// transposed through a per-warp shared-memory tile (stride D = 15 or 12 words: odd / 4-bank
-// patterns, conflict-free for 15) and leave the SM as one bulk async copy per warp per step
-// (cp.async.bulk shared -> global, 32*D*4 contiguous bytes) instead of D strided 4-byte
-// stores per thread.
+// transposed through a per-warp shared-memory tile (stride D = 15 or 12 words; 15 is odd, so the
+// 32 lanes hit 32 different banks) and leave the SM as 128-bit fully coalesced stores over the
+// warp's 32*D contiguous floats instead of D strided 4-byte stores per thread.
 #pragma once
 #include "env_core.cuh"
 
@@ -45,40 +44,66 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
 }
 
-// One warp's 32 observations: registers -> smem tile -> global (bulk async copy when the
-// destination is 16-byte aligned and the warp is full, coalesced scalar stores otherwise).
+#ifndef DRONECU_EMIT_BULK
+#define DRONECU_EMIT_BULK 0
+#endif
+#ifndef DRONECU_MIN_BLOCKS
+#define DRONECU_MIN_BLOCKS 4   // <= 64 registers/thread: 4 CTAs of 256 threads per SM (ncu: round-1 notes)
+#endif
+
+// One warp's 32 observations: registers -> per-warp smem tile (stride D words) -> global as
+// 128-bit coalesced stores (lane j moves quad j, j+32, ... of the 32*D contiguous floats).
+// profiles/README.md (round 1) has the ncu comparison with the cp.async.bulk variant
+// (-DDRONECU_EMIT_BULK=1): the kernel is issue-bound and the async-proxy fence + elect + UBLKCP
+// sequence costs more issue slots per warp-step than 4 LDS.128 + 4 STG.128.
 template <int OBS_DIM>
 __device__ __forceinline__ void emit_obs_rows(float* tile, float* gdst, const EnvState& s, int lane,
                                               int valid, bool active) {
+  constexpr int kQuads = 32 * OBS_DIM / 4;
+  const bool aligned = (valid == 32) && ((reinterpret_cast<uintptr_t>(gdst) & 15) == 0);
+#if DRONECU_EMIT_BULK
   constexpr uint32_t kBytes = 32 * OBS_DIM * sizeof(float);
-  // the previous bulk copy must have finished READING the tile before it is overwritten
   if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   __syncwarp();
   if (active) write_obs<OBS_DIM>(tile + lane * OBS_DIM, s);
-  const bool bulk = (valid == 32) && ((reinterpret_cast<uintptr_t>(gdst) & 15) == 0);
-  if (bulk) {
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy
+  if (aligned) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
     if (lane == 0) {
       asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                    :: "l"(gdst), "r"(smem_u32(tile)), "r"(kBytes) : "memory");
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
-  } else {
-    __syncwarp();
-    for (int j = lane; j < valid * OBS_DIM; j += 32) gdst[j] = tile[j];
-    __syncwarp();
+    return;
   }
+#else
+  __syncwarp();     // the previous step's read-back of this tile is complete
+  if (active) write_obs<OBS_DIM>(tile + lane * OBS_DIM, s);
+  if (aligned) {
+    __syncwarp();
+    const float4* t4 = reinterpret_cast<const float4*>(tile);
+    float4* g4 = reinterpret_cast<float4*>(gdst);
+#pragma unroll
+    for (int j = lane; j < kQuads; j += 32) st_quad(g4 + j, t4[j]);
+    return;
+  }
+#endif
+  __syncwarp();
+  for (int j = lane; j < valid * OBS_DIM; j += 32) gdst[j] = tile[j];
+  __syncwarp();
 }
 
-template <int OBS_DIM, bool RANDOMIZED, bool AUTORESET, int ACT_MODE>
-__global__ void __launch_bounds__(kBlock) rollout_kernel(const __grid_constant__ RolloutArgs A) {
+// RECORD = true: the "rollout record" output set -- next_obs, reward, done (and the applied action
+// when it is generated in-kernel) are all present, nothing else is: no per-step null checks.
+// RECORD = false: every output pointer is optional (the VecEnv.step boundary with its info arrays).
+template <int OBS_DIM, bool RANDOMIZED, bool AUTORESET, int ACT_MODE, bool RECORD>
+__global__ void __launch_bounds__(kBlock, DRONECU_MIN_BLOCKS) rollout_kernel(const __grid_constant__ RolloutArgs A) {
   __shared__ __align__(128) float tiles[kWarps][32 * OBS_DIM];
   __shared__ unsigned long long blk_stats[3];
   __shared__ double blk_ret;
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t warp_base = (int64_t)blockIdx.x * kBlock + warp * 32;
+  const int64_t warp_base = (int64_t)blockIdx.x * blockDim.x + warp * 32;
   const int64_t i = warp_base + lane;
   const bool active = i < A.n;
   const int valid = (int)max((int64_t)0, min((int64_t)32, A.n - warp_base));
@@ -98,36 +123,53 @@ __global__ void __launch_bounds__(kBlock) rollout_kernel(const __grid_constant__
   uint32_t n_done = 0, n_term = 0, len_sum = 0;
   float ret_sum = 0.f;
 
+  // running output pointers: one 64-bit add per output per step instead of k*n + i each time
+  const int64_t n = A.n;
+  const float4* p_act_in = A.actions + i;
+  float4* p_act_out = A.out_actions + i;
+  float* p_rew = A.reward + i;
+  uint8_t* p_done = A.done + i;
+  uint8_t* p_trunc = A.truncated + i;
+  float* p_obs = A.next_obs + warp_base * OBS_DIM;
+  int64_t row = 0;                                   // only used by the rare "where done" outputs
+  const bool w_act = RECORD ? (ACT_MODE == 1) : (A.out_actions != nullptr);
+  const bool w_rew = RECORD || (A.reward != nullptr);
+  const bool w_done = RECORD || (A.done != nullptr);
+  const bool w_trunc = !RECORD && (A.truncated != nullptr);
+  const bool w_obs = RECORD || (A.next_obs != nullptr);
+  const float act_scale = P.motor_max * 5.9604644775390625e-8f;   // exact: a power of two times motor_max
+
   float4 act = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (ACT_MODE == 0 && active) act = ld_quad_nc(A.actions + i);
+  if (ACT_MODE == 0 && active) act = ld_quad_nc(p_act_in);
 
   for (int k = 0; k < A.K; ++k) {
-    const int64_t row = (int64_t)k * A.n;
     float4 f = act;
     if constexpr (ACT_MODE == 0) {
-      // software prefetch of the next step's action quad
-      if (active && k + 1 < A.K) act = ld_quad_nc(A.actions + row + A.n + i);
+      p_act_in += n;
+      if (active && k + 1 < A.K) act = ld_quad_nc(p_act_in);     // software prefetch of the next quad
     } else {
       const uint4 w = env_stream(P.seed, env_id, A.t0 + (uint64_t)k, STREAM_ACTION);
-      f = make_float4(u01(w.x) * P.motor_max, u01(w.y) * P.motor_max, u01(w.z) * P.motor_max,
-                      u01(w.w) * P.motor_max);
+      f = make_float4((float)(w.x >> 8) * act_scale, (float)(w.y >> 8) * act_scale,
+                      (float)(w.z >> 8) * act_scale, (float)(w.w >> 8) * act_scale);
     }
     const StepResult r = step_env(s, P, f);
     const bool done = r.crashed || r.timeout;
 
     if (active) {
-      if (A.out_actions != nullptr) st_quad(A.out_actions + row + i, f);
-      if (A.reward != nullptr) A.reward[row + i] = r.reward;
-      if (A.done != nullptr) A.done[row + i] = done ? 1 : 0;
-      if (A.truncated != nullptr) A.truncated[row + i] = (r.timeout && !r.crashed) ? 1 : 0;
+      if (w_act) st_quad(p_act_out, f);
+      if (w_rew) *p_rew = r.reward;
+      if (w_done) *p_done = done ? 1 : 0;
+      if (w_trunc) *p_trunc = (r.timeout && !r.crashed) ? 1 : 0;
       if (done) {
         n_done += 1;
         n_term += r.crashed ? 1 : 0;
         len_sum += (uint32_t)s.ep_len;
         ret_sum += s.ep_ret;
-        if (A.terminal_obs != nullptr) write_obs<OBS_DIM>(A.terminal_obs + (row + i) * OBS_DIM, s);
-        if (A.episode_r != nullptr) A.episode_r[row + i] = s.ep_ret;
-        if (A.episode_l != nullptr) A.episode_l[row + i] = s.ep_len;
+        if constexpr (!RECORD) {
+          if (A.terminal_obs != nullptr) write_obs<OBS_DIM>(A.terminal_obs + (row + i) * OBS_DIM, s);
+          if (A.episode_r != nullptr) A.episode_r[row + i] = s.ep_ret;
+          if (A.episode_l != nullptr) A.episode_l[row + i] = s.ep_len;
+        }
         if constexpr (AUTORESET) {
           reset_env<RANDOMIZED>(s, P, env_id);
         } else {
@@ -136,8 +178,8 @@ __global__ void __launch_bounds__(kBlock) rollout_kernel(const __grid_constant__
         }
       }
     }
-    if (A.next_obs != nullptr && valid > 0)
-      emit_obs_rows<OBS_DIM>(tile, A.next_obs + (row + warp_base) * OBS_DIM, s, lane, valid, active);
+    if (w_obs && valid > 0) emit_obs_rows<OBS_DIM>(tile, p_obs, s, lane, valid, active);
+    p_act_out += n; p_rew += n; p_done += n; p_trunc += n; p_obs += n * OBS_DIM; row += n;
   }
 
   if (active) store_state(A.state, i, s);
@@ -166,8 +208,9 @@ __global__ void __launch_bounds__(kBlock) rollout_kernel(const __grid_constant__
     atomicAdd(&slot->length_sum, blk_stats[2]);
     atomicAdd(&slot->return_sum, blk_ret);
   }
-  // the shared tile must stay alive until the bulk engine has read it
-  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+#if DRONECU_EMIT_BULK
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // tile must outlive the copy
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -179,7 +222,7 @@ __global__ void __launch_bounds__(kBlock) reset_kernel(StatePlanes sp, const __g
                                                        int zero_first) {
   __shared__ __align__(128) float tiles[kWarps][32 * OBS_DIM];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t warp_base = (int64_t)blockIdx.x * kBlock + warp * 32;
+  const int64_t warp_base = (int64_t)blockIdx.x * blockDim.x + warp * 32;
   const int64_t i = warp_base + lane;
   const bool active = i < n;
   const int valid = (int)max((int64_t)0, min((int64_t)32, n - warp_base));
@@ -193,7 +236,9 @@ __global__ void __launch_bounds__(kBlock) reset_kernel(StatePlanes sp, const __g
   }
   if (obs != nullptr && valid > 0)
     emit_obs_rows<OBS_DIM>(tiles[warp], obs + warp_base * OBS_DIM, s, lane, valid, active);
+#if DRONECU_EMIT_BULK
   if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -7,7 +7,7 @@
 
 namespace dronecu {
 
-enum : uint32_t { STREAM_RESET_A = 0, STREAM_RESET_B = 1, STREAM_ACTION = 2, STREAM_NOISE = 3 };
+enum : uint32_t { STREAM_RESET = 0, STREAM_ACTION = 2, STREAM_NOISE = 3 };
 
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1) {
   constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;

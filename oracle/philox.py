@@ -13,8 +13,10 @@ tests/test_philox.py.
 Stream convention (must match drone_rl_b200/csrc/philox.cuh):
     key     = (seed & 0xffffffff, seed >> 32)
     counter = (env_id & 0xffffffff, env_id >> 32, index, stream)
-    stream 0 (RESET_A) index = ep_num of the new episode -> words = pos.x, pos.y, tgt.x, tgt.y
-    stream 1 (RESET_B) index = ep_num                    -> word 0 = tgt.z
+    stream 0 (RESET)   index = ep_num of the new episode -> the top 24 bits of the four words give
+                       pos.x, pos.y, tgt.x, tgt.y; the fifth uniform (tgt.z) is assembled from the
+                       otherwise unused low bytes of words 0..2: (w0&255) | (w1&255)<<8 | (w2&255)<<16
+                       (one Philox call per reset: 120 of its 128 random bits are used)
     stream 2 (ACTION)  index = global step t             -> 4 motor uniforms (random policy)
     stream 3 (NOISE)   index = global step t             -> 4 uniforms -> 4 Box-Muller normals
     uniform u = (word >> 8) * 2**-24  in [0, 1)   (exact in both float32 and float64)
@@ -28,8 +30,7 @@ M1 = np.uint64(0xCD9E8D57)
 W0 = 0x9E3779B9
 W1 = 0xBB67AE85
 
-STREAM_RESET_A = 0
-STREAM_RESET_B = 1
+STREAM_RESET = 0
 STREAM_ACTION = 2
 STREAM_NOISE = 3
 
@@ -76,9 +77,14 @@ def env_stream(seed: int, env_ids, index, stream: int):
 
 def reset_uniforms(seed: int, env_ids, ep_num):
     """The five reset uniforms [5, n] in the reference's draw order (drone.py:57, :73)."""
-    a = env_stream(seed, env_ids, ep_num, STREAM_RESET_A)
-    b = env_stream(seed, env_ids, ep_num, STREAM_RESET_B)
-    return np.concatenate([a, b[:1]], axis=0)
+    env_ids = np.asarray(env_ids, dtype=np.uint64)
+    idx = np.asarray(ep_num, dtype=np.uint64)
+    c3 = (np.uint64(STREAM_RESET) | ((idx >> _SH32) << np.uint64(8))) & _MASK32
+    w = philox4x32_10(env_ids & _MASK32, env_ids >> _SH32, idx & _MASK32, c3,
+                      seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    lo = (w[0] & np.uint32(255)) | ((w[1] & np.uint32(255)) << np.uint32(8)) | ((w[2] & np.uint32(255)) << np.uint32(16))
+    fifth = lo.astype(np.float64) * (2.0 ** -24)
+    return np.stack([u01(w[0]), u01(w[1]), u01(w[2]), u01(w[3]), fifth])
 
 
 def action_uniforms(seed: int, env_ids, t):
