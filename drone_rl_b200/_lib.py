@@ -54,6 +54,22 @@ class StateView(C.Structure):
                 ("d_ep_num", C.c_void_p), ("d_ep_len", C.c_void_p), ("d_ep_ret", C.c_void_p)]
 
 
+class PolicyOut(C.Structure):
+    _fields_ = [("d_obs", C.c_void_p), ("d_actions", C.c_void_p), ("d_logp", C.c_void_p), ("d_value", C.c_void_p),
+                ("d_reward", C.c_void_p), ("d_done", C.c_void_p), ("d_last_value", C.c_void_p),
+                ("d_last_obs", C.c_void_p)]
+
+
+class PPOConfig(C.Structure):
+    _fields_ = [("learning_rate", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("adam_eps", C.c_float),
+                ("clip_range", C.c_float), ("vf_coef", C.c_float), ("ent_coef", C.c_float),
+                ("max_grad_norm", C.c_float)]
+
+
+POLICY_PARAMS = 10697
+GRAD_LEN = POLICY_PARAMS + 8
+
+
 class Stats(C.Structure):
     _fields_ = [("episodes", C.c_uint64), ("terminated", C.c_uint64), ("truncated", C.c_uint64),
                 ("length_sum", C.c_uint64), ("return_sum", C.c_double), ("env_steps", C.c_uint64)]
@@ -71,6 +87,7 @@ _SIGNATURES = {
     "dronecu_num_envs": (C.c_int64, [_P]),
     "dronecu_obs_dim": (C.c_int, [_P]),
     "dronecu_global_step": (C.c_int64, [_P]),
+    "dronecu_set_global_step": (C.c_int, [_P, C.c_int64]),
     "dronecu_motor_max": (C.c_double, [_P]),
     "dronecu_launch_count": (C.c_uint64, [_P]),
     "dronecu_reset": (C.c_int, [_P, _P, _P, _P]),
@@ -83,6 +100,19 @@ _SIGNATURES = {
     "dronecu_get_state_host": (C.c_int, [_P, C.POINTER(StateView)]),
     "dronecu_set_state_host": (C.c_int, [_P, C.POINTER(StateView)]),
     "dronecu_episode_stats": (C.c_int, [_P, C.POINTER(Stats), C.c_int]),
+    # PPO half
+    "dronecu_rollout_policy": (C.c_int, [_P, C.c_int, _P, C.c_int, C.POINTER(PolicyOut), _P]),
+    "dronecu_policy_forward": (C.c_int, [C.c_int, C.c_int64, _P, _P, _P, _P, _P]),
+    "dronecu_gae": (C.c_int, [C.c_int, C.c_int, C.c_int64, _P, _P, _P, _P, C.c_float, C.c_float, _P, _P, _P]),
+    "dronecu_ppo_config_default": (None, [C.POINTER(PPOConfig)]),
+    "dronecu_ppo_create": (C.c_int, [C.POINTER(PPOConfig), C.c_int, C.POINTER(_P)]),
+    "dronecu_ppo_destroy": (C.c_int, [_P]),
+    "dronecu_ppo_adv_stats": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, _P, _P]),
+    "dronecu_ppo_grad": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int64, C.c_float, C.c_float, _P, _P, _P]),
+    "dronecu_ppo_apply": (C.c_int, [_P, _P, _P, C.c_double, _P, _P]),
+    "dronecu_ppo_num_updates": (C.c_int64, [_P]),
+    "dronecu_ppo_get_state": (C.c_int, [_P, _P, C.POINTER(C.c_int64), _P]),
+    "dronecu_ppo_set_state": (C.c_int, [_P, _P, C.c_int64, _P]),
 }
 
 _lib = None

@@ -128,6 +128,10 @@ class DroneBatch:
     def global_step(self) -> int:
         return int(self.lib.dronecu_global_step(self._h))
 
+    @global_step.setter
+    def global_step(self, t: int):
+        _lib.check(self.lib.dronecu_set_global_step(self._h, int(t)), "dronecu_set_global_step")
+
     @property
     def launch_count(self) -> int:
         return int(self.lib.dronecu_launch_count(self._h))

@@ -12,6 +12,7 @@
 #include "../../include/dronecu.h"
 #include "capi_common.h"
 #include "env_kernels.cuh"
+#include "env_handle.h"
 
 using namespace dronecu;
 
@@ -19,27 +20,6 @@ namespace dronecu {
 thread_local std::string g_last_error;
 void set_error(const std::string& s) { g_last_error = s; }
 }  // namespace dronecu
-
-struct dronecu_env {
-  dronecu_config cfg;
-  EnvParams P;
-  int device;
-  int64_t n;
-  uint64_t t;          // global step index (Philox counter for ACTION / NOISE streams)
-  float4* planes;      // 5 * n quads
-  StatePlanes sp;
-  StatSlot* stats;
-  uint64_t launches;
-  uint64_t env_steps;
-  // device + stream used by the *_host entry points (lazily created)
-  cudaStream_t io_stream;
-  float *d_act, *d_obs, *d_rew, *d_term;
-  uint8_t *d_done, *d_trunc, *d_mask;
-  float* d_ep_r;
-  int32_t* d_ep_l;
-  float *d_view_f;     // 16 floats per env scratch for get/set_state_host
-  int32_t* d_view_i;   // 3 ints per env
-};
 
 extern "C" int dronecu_version(void) { return DRONECU_VERSION; }
 extern "C" const char* dronecu_last_error(void) { return g_last_error.c_str(); }
@@ -201,6 +181,11 @@ extern "C" int dronecu_destroy(dronecu_env* e) {
 extern "C" int64_t dronecu_num_envs(const dronecu_env* e) { return e ? e->n : 0; }
 extern "C" int dronecu_obs_dim(const dronecu_env* e) { return e ? e->cfg.obs_dim : 0; }
 extern "C" int64_t dronecu_global_step(const dronecu_env* e) { return e ? (int64_t)e->t : 0; }
+extern "C" int dronecu_set_global_step(dronecu_env* e, int64_t t) {
+  if (!e || t < 0) return fail(DRONECU_ERR_INVALID, "bad argument");
+  e->t = (uint64_t)t;
+  return DRONECU_OK;
+}
 extern "C" double dronecu_motor_max(const dronecu_env* e) { return e ? 3.0 * e->cfg.mass * e->cfg.gravity / 4.0 : 0.0; }
 extern "C" uint64_t dronecu_launch_count(const dronecu_env* e) { return e ? e->launches : 0; }
 

@@ -1,0 +1,200 @@
+// C ABI of the PPO half of libdronecu.so (include/dronecu.h): in-kernel policy rollout, GAE,
+// minibatch gradient, clip + Adam.  Plain pointers, no torch types, no CPU fallback.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "../../include/dronecu.h"
+#include "capi_common.h"
+#include "env_handle.h"
+#include "ppo_update.cuh"
+
+using namespace dronecu;
+
+static_assert(kParams == DRONECU_POLICY_PARAMS, "header / kernel parameter count mismatch");
+static_assert(kGradLen == DRONECU_GRAD_LEN, "header / kernel gradient length mismatch");
+
+struct dronecu_ppo {
+  dronecu_ppo_config cfg;
+  int device;
+  int n_sm;
+  float* partials;   // [n_sm, kGradLen]
+  float* moments;    // [2, kParams]  Adam m | v
+  int64_t step;
+  uint64_t launches;
+};
+
+extern "C" int dronecu_rollout_policy(dronecu_env* e, int K, const float* d_params, int deterministic,
+                                      const dronecu_policy_out* out, void* stream) {
+  if (!e || !d_params) return fail(DRONECU_ERR_INVALID, "dronecu_rollout_policy: null argument");
+  if (K <= 0) return fail(DRONECU_ERR_INVALID, "K must be positive");
+  if (e->cfg.obs_dim != 15 || !(e->cfg.flags & DRONECU_AUTORESET))
+    return fail(DRONECU_ERR_UNSUPPORTED, "policy rollout needs the 15-dim observation and DRONECU_AUTORESET");
+  if (out && out->d_actions && (reinterpret_cast<uintptr_t>(out->d_actions) & 15))
+    return fail(DRONECU_ERR_INVALID, "out->d_actions must be 16-byte aligned");
+  DeviceGuard guard(e->device);
+  PolicyArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.state = e->sp; a.P = e->P; a.n = e->n; a.K = K; a.t0 = e->t; a.theta = d_params; a.deterministic = deterministic;
+  a.stats = e->stats;
+  if (out) {
+    a.obs = out->d_obs; a.actions = reinterpret_cast<float4*>(out->d_actions); a.logp = out->d_logp;
+    a.value = out->d_value; a.reward = out->d_reward; a.done = out->d_done; a.last_value = out->d_last_value;
+    a.last_obs = out->d_last_obs;
+  }
+  const unsigned grid = (unsigned)((e->n + kPolBlock - 1) / kPolBlock);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (e->cfg.flags & DRONECU_RANDOMIZED) {
+    CUDA_TRY(cudaFuncSetAttribute(policy_rollout_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPolicySmem));
+    policy_rollout_kernel<true><<<grid, kPolBlock, kPolicySmem, st>>>(a);
+  } else {
+    CUDA_TRY(cudaFuncSetAttribute(policy_rollout_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPolicySmem));
+    policy_rollout_kernel<false><<<grid, kPolBlock, kPolicySmem, st>>>(a);
+  }
+  e->launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  e->t += (uint64_t)K;
+  e->env_steps += (uint64_t)K * (uint64_t)e->n;
+  return DRONECU_OK;
+}
+
+extern "C" int dronecu_policy_forward(int device, int64_t B, const float* d_params, const float* d_obs, float* d_mean,
+                                      float* d_value, void* stream) {
+  if (B <= 0 || !d_params || !d_obs) return fail(DRONECU_ERR_INVALID, "dronecu_policy_forward: bad argument");
+  if (d_mean && (reinterpret_cast<uintptr_t>(d_mean) & 15)) return fail(DRONECU_ERR_INVALID, "d_mean must be 16-byte aligned");
+  DeviceGuard guard(device);
+  CUDA_TRY(cudaFuncSetAttribute(policy_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MlpSmem)));
+  const unsigned grid = (unsigned)std::min<int64_t>((B + kPolBlock - 1) / kPolBlock, 148 * 4);
+  policy_forward_kernel<<<grid, kPolBlock, sizeof(MlpSmem), (cudaStream_t)stream>>>(d_params, d_obs, B, reinterpret_cast<float4*>(d_mean), d_value);
+  CUDA_TRY(cudaGetLastError());
+  return DRONECU_OK;
+}
+
+extern "C" int dronecu_gae(int device, int K, int64_t n, const float* d_reward, const float* d_value,
+                           const uint8_t* d_done, const float* d_last_value, float gamma, float lam,
+                           float* d_adv, float* d_ret, void* stream) {
+  if (K <= 0 || n <= 0 || !d_reward || !d_value || !d_done || !d_last_value || !d_adv || !d_ret)
+    return fail(DRONECU_ERR_INVALID, "dronecu_gae: bad argument");
+  DeviceGuard guard(device);
+  gae_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(K, n, d_reward, d_value, d_done,
+                                                                           d_last_value, gamma, lam, d_adv, d_ret);
+  CUDA_TRY(cudaGetLastError());
+  return DRONECU_OK;
+}
+
+extern "C" void dronecu_ppo_config_default(dronecu_ppo_config* c) {
+  c->learning_rate = 3e-4f; c->beta1 = 0.9f; c->beta2 = 0.999f; c->adam_eps = 1e-5f;
+  c->clip_range = 0.2f; c->vf_coef = 0.5f; c->ent_coef = 0.0f; c->max_grad_norm = 0.5f;
+}
+
+extern "C" int dronecu_ppo_create(const dronecu_ppo_config* cfg, int device, dronecu_ppo** out) {
+  if (!cfg || !out) return fail(DRONECU_ERR_INVALID, "dronecu_ppo_create: null argument");
+  int ndev = 0;
+  cudaError_t err = cudaGetDeviceCount(&ndev);
+  if (err != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(DRONECU_ERR_CUDA, std::string("no CUDA device (there is no CPU fallback): ") + cudaGetErrorString(err));
+  }
+  if (device < 0 || device >= ndev) return fail(DRONECU_ERR_INVALID, "device index out of range");
+  DeviceGuard guard(device);
+  dronecu_ppo* p = new (std::nothrow) dronecu_ppo();
+  if (!p) return fail(DRONECU_ERR_ALLOC, "host allocation failed");
+  std::memset(p, 0, sizeof(*p));
+  p->cfg = *cfg; p->device = device;
+  CUDA_TRY(cudaDeviceGetAttribute(&p->n_sm, cudaDevAttrMultiProcessorCount, device));
+  CUDA_TRY(cudaMalloc(&p->partials, sizeof(float) * (size_t)p->n_sm * kGradLen));
+  CUDA_TRY(cudaMalloc(&p->moments, sizeof(float) * 2 * kParams));
+  CUDA_TRY(cudaMemset(p->moments, 0, sizeof(float) * 2 * kParams));
+  CUDA_TRY(cudaFuncSetAttribute(ppo_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UpdSmem)));
+  *out = p;
+  return DRONECU_OK;
+}
+
+extern "C" int dronecu_ppo_destroy(dronecu_ppo* p) {
+  if (!p) return DRONECU_OK;
+  DeviceGuard guard(p->device);
+  cudaDeviceSynchronize();
+  cudaFree(p->partials); cudaFree(p->moments);
+  cudaGetLastError();
+  delete p;
+  return DRONECU_OK;
+}
+
+extern "C" int64_t dronecu_ppo_num_updates(const dronecu_ppo* p) { return p ? p->step : 0; }
+
+extern "C" int dronecu_ppo_adv_stats(dronecu_ppo* p, const float* d_adv, const int32_t* d_index, int64_t first,
+                                     int64_t m, double* d_out, void* stream) {
+  if (!p || !d_adv || !d_out || m <= 0) return fail(DRONECU_ERR_INVALID, "dronecu_ppo_adv_stats: bad argument");
+  DeviceGuard guard(p->device);
+  const unsigned grid = (unsigned)std::min<int64_t>((m + 255) / 256, (int64_t)p->n_sm * 8);
+  adv_stats_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_adv, d_index, first, m, d_out);
+  p->launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  return DRONECU_OK;
+}
+
+extern "C" int dronecu_ppo_grad(dronecu_ppo* p, const float* d_params, const float* d_obs, const float* d_actions,
+                                const float* d_old_logp, const float* d_adv, const float* d_returns,
+                                const int32_t* d_index, int64_t first, int64_t m, float adv_mean, float adv_inv_std,
+                                const double* d_adv_stats, float* d_grad, void* stream) {
+  if (!p || !d_params || !d_obs || !d_actions || !d_old_logp || !d_adv || !d_returns || !d_grad || m <= 0)
+    return fail(DRONECU_ERR_INVALID, "dronecu_ppo_grad: bad argument");
+  if (reinterpret_cast<uintptr_t>(d_actions) & 15) return fail(DRONECU_ERR_INVALID, "d_actions must be 16-byte aligned");
+  DeviceGuard guard(p->device);
+  UpdArgs a;
+  a.theta = d_params; a.obs = d_obs; a.actions = reinterpret_cast<const float4*>(d_actions); a.old_logp = d_old_logp;
+  a.adv = d_adv; a.ret = d_returns; a.index = d_index; a.first = first; a.m = m;
+  a.adv_mean = adv_mean; a.adv_inv_std = adv_inv_std; a.adv_stats = d_adv_stats;
+  a.clip = p->cfg.clip_range; a.vf_coef = p->cfg.vf_coef; a.ent_coef = p->cfg.ent_coef;
+  a.partials = p->partials;
+  const int64_t tiles = (m + kUpdBlock - 1) / kUpdBlock;
+  const unsigned grid = (unsigned)std::min<int64_t>(tiles, p->n_sm);
+  cudaStream_t st = (cudaStream_t)stream;
+  ppo_grad_kernel<<<grid, kUpdBlock, sizeof(UpdSmem), st>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  ppo_reduce_kernel<<<(kGradLen + 255) / 256, 256, 0, st>>>(p->partials, (int)grid, d_grad);
+  CUDA_TRY(cudaGetLastError());
+  p->launches += 2;
+  return DRONECU_OK;
+}
+
+extern "C" int dronecu_ppo_apply(dronecu_ppo* p, float* d_params, const float* d_grad, double inv_count,
+                                 float* d_info, void* stream) {
+  if (!p || !d_params || !d_grad || !(inv_count > 0)) return fail(DRONECU_ERR_INVALID, "dronecu_ppo_apply: bad argument");
+  DeviceGuard guard(p->device);
+  p->step += 1;
+  const double b1 = p->cfg.beta1, b2 = p->cfg.beta2;
+  const double bc1 = 1.0 - std::pow(b1, (double)p->step), bc2 = 1.0 - std::pow(b2, (double)p->step);
+  AdamArgs a;
+  a.theta = d_params; a.grad = d_grad; a.m = p->moments; a.v = p->moments + kParams;
+  a.inv_count = (float)inv_count;
+  a.lr_over_bc1 = (float)(p->cfg.learning_rate / bc1);
+  a.inv_sqrt_bc2 = (float)(1.0 / std::sqrt(bc2));
+  a.beta1 = p->cfg.beta1; a.beta2 = p->cfg.beta2; a.eps = p->cfg.adam_eps; a.max_norm = p->cfg.max_grad_norm;
+  a.info = d_info;
+  ppo_apply_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(a);
+  p->launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  return DRONECU_OK;
+}
+
+extern "C" int dronecu_ppo_get_state(dronecu_ppo* p, float* d_moments, int64_t* h_step, void* stream) {
+  if (!p) return fail(DRONECU_ERR_INVALID, "null handle");
+  DeviceGuard guard(p->device);
+  if (d_moments)
+    CUDA_TRY(cudaMemcpyAsync(d_moments, p->moments, sizeof(float) * 2 * kParams, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  if (h_step) *h_step = p->step;
+  return DRONECU_OK;
+}
+
+extern "C" int dronecu_ppo_set_state(dronecu_ppo* p, const float* d_moments, int64_t step, void* stream) {
+  if (!p || step < 0) return fail(DRONECU_ERR_INVALID, "bad argument");
+  DeviceGuard guard(p->device);
+  if (d_moments)
+    CUDA_TRY(cudaMemcpyAsync(p->moments, d_moments, sizeof(float) * 2 * kParams, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  p->step = step;
+  return DRONECU_OK;
+}

@@ -249,7 +249,7 @@ struct StateView {
   int32_t *step, *ep_num, *ep_len;
 };
 
-__global__ void get_state_kernel(StatePlanes sp, int64_t n, StateView v) {
+static __global__ void get_state_kernel(StatePlanes sp, int64_t n, StateView v) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const EnvState s = load_state(sp, i);
@@ -264,7 +264,7 @@ __global__ void get_state_kernel(StatePlanes sp, int64_t n, StateView v) {
   if (v.ep_ret) v.ep_ret[i] = s.ep_ret;
 }
 
-__global__ void set_state_kernel(StatePlanes sp, int64_t n, StateView v) {
+static __global__ void set_state_kernel(StatePlanes sp, int64_t n, StateView v) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   EnvState s = load_state(sp, i);

@@ -1,0 +1,291 @@
+// K-step rollout with the PPO policy / value MLP evaluated inside the step loop (float32 CUDA-core
+// version: one env per thread, the 10,697 parameters transposed once per CTA into shared memory and
+// read back as warp-broadcast 128-bit loads -- every lane multiplies the same weight by its own
+// env's activation).  What SB3's collect_rollouts does per step (call site
+// /root/reference/train.py:63-68): a, v, logp = policy(obs); env.step(clip(a)); buffer.add(obs, a,
+// r, episode_start, v, logp) -- here for K steps without the state or the activations ever leaving
+// the SM.
+#pragma once
+#include "env_kernels.cuh"
+#include "ppo_common.cuh"
+
+namespace dronecu {
+
+constexpr int kPolBlock = 128;
+
+// shared-memory image of the parameters, transposed to [in][out] so a thread walks the inputs of a
+// layer and fetches 4 output weights per LDS.128
+struct alignas(16) MlpSmem {
+  float W1T[2][kObs][kHid];
+  float b1[2][kHid];
+  float W2T[2][kHid][kHid];
+  float b2[2][kHid];
+  float W3piT[kHid][kAct];
+  float W3vf[kHid];
+  float b3pi[kAct];
+  float b3vf, pad[3];
+  float log_std[kAct];
+};
+
+constexpr size_t kPolicySmem = sizeof(MlpSmem) + (kPolBlock / 32) * 32 * kObs * sizeof(float);
+
+__device__ __forceinline__ void load_mlp_smem(MlpSmem& S, const float* __restrict__ theta) {
+  for (int idx = threadIdx.x; idx < kParams; idx += blockDim.x) {
+    const float v = theta[idx];
+    int o = idx, t = 0;
+    if (o >= O_VF_W1 && o < O_LOGSTD) { t = 1; o -= kTowerStride; }
+    if (idx >= O_LOGSTD) { S.log_std[idx - O_LOGSTD] = v; continue; }
+    if (o < O_PI_B1) { S.W1T[t][o % kObs][o / kObs] = v; }
+    else if (o < O_PI_W2) { S.b1[t][o - O_PI_B1] = v; }
+    else if (o < O_PI_B2) { const int q = o - O_PI_W2; S.W2T[t][q % kHid][q / kHid] = v; }
+    else if (o < O_PI_W3) { S.b2[t][o - O_PI_B2] = v; }
+    else if (t == 0) {
+      if (o < O_PI_B3) { const int q = o - O_PI_W3; S.W3piT[q % kHid][q / kHid] = v; }
+      else S.b3pi[o - O_PI_B3] = v;
+    } else {
+      // vf head: W3 [1,64] then b3 [1]; offsets relative to the pi block layout
+      const int q = idx - O_VF_W3;
+      if (q < kHid) S.W3vf[q] = v; else S.b3vf = v;
+    }
+  }
+}
+
+// one tower for one env: x[15] -> NOUT outputs.  h1 stays in registers; layer 2 is produced in four
+// chunks of 16 units that are consumed by the head immediately, so h2 is never materialised.
+template <int NOUT>
+__device__ __forceinline__ void tower_forward(const MlpSmem& S, const int t, const float (&x)[kObs], float (&out)[NOUT]) {
+  float h1[kHid];
+#pragma unroll
+  for (int q = 0; q < kHid / 4; ++q) {
+    const float4 b = reinterpret_cast<const float4*>(S.b1[t])[q];
+    h1[4 * q] = b.x; h1[4 * q + 1] = b.y; h1[4 * q + 2] = b.z; h1[4 * q + 3] = b.w;
+  }
+#pragma unroll
+  for (int i = 0; i < kObs; ++i) {
+    const float xi = x[i];
+#pragma unroll
+    for (int q = 0; q < kHid / 4; ++q) {
+      const float4 w = reinterpret_cast<const float4*>(S.W1T[t][i])[q];
+      h1[4 * q] = fmaf(w.x, xi, h1[4 * q]); h1[4 * q + 1] = fmaf(w.y, xi, h1[4 * q + 1]);
+      h1[4 * q + 2] = fmaf(w.z, xi, h1[4 * q + 2]); h1[4 * q + 3] = fmaf(w.w, xi, h1[4 * q + 3]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kHid; ++j) h1[j] = tanh_fast(h1[j]);
+
+  if constexpr (NOUT == kAct) {
+#pragma unroll
+    for (int o = 0; o < kAct; ++o) out[o] = S.b3pi[o];
+  } else {
+    out[0] = S.b3vf;
+  }
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    float acc[16];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 b = reinterpret_cast<const float4*>(S.b2[t] + 16 * c)[q];
+      acc[4 * q] = b.x; acc[4 * q + 1] = b.y; acc[4 * q + 2] = b.z; acc[4 * q + 3] = b.w;
+    }
+#pragma unroll
+    for (int i = 0; i < kHid; ++i) {
+      const float hi = h1[i];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 w = reinterpret_cast<const float4*>(S.W2T[t][i] + 16 * c)[q];
+        acc[4 * q] = fmaf(w.x, hi, acc[4 * q]); acc[4 * q + 1] = fmaf(w.y, hi, acc[4 * q + 1]);
+        acc[4 * q + 2] = fmaf(w.z, hi, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(w.w, hi, acc[4 * q + 3]);
+      }
+    }
+#pragma unroll
+    for (int jj = 0; jj < 16; ++jj) {
+      const float a = tanh_fast(acc[jj]);
+      if constexpr (NOUT == kAct) {
+        const float4 w = reinterpret_cast<const float4*>(S.W3piT[16 * c + jj])[0];
+        out[0] = fmaf(w.x, a, out[0]); out[1] = fmaf(w.y, a, out[1]);
+        out[2] = fmaf(w.z, a, out[2]); out[3] = fmaf(w.w, a, out[3]);
+      } else {
+        out[0] = fmaf(S.W3vf[16 * c + jj], a, out[0]);
+      }
+    }
+  }
+}
+
+struct PolicyArgs {
+  StatePlanes state;
+  EnvParams P;
+  int64_t n;
+  int32_t K;
+  uint64_t t0;
+  const float* theta;     // [kParams]
+  int32_t deterministic;  // != 0: action = mean (SB3 predict(deterministic=True), test.py:14)
+  float* obs;             // [K,n,15] observation the action was computed from
+  float4* actions;        // [K,n]    sampled action, NOT clipped (what SB3 stores in the buffer)
+  float* logp;            // [K,n]
+  float* value;           // [K,n]
+  float* reward;          // [K,n]
+  uint8_t* done;          // [K,n]
+  float* last_value;      // [n]      V(observation after the K-th step)
+  float* last_obs;        // [n,15]
+  StatSlot* stats;
+};
+
+template <bool RANDOMIZED>
+__global__ void __launch_bounds__(kPolBlock) policy_rollout_kernel(const __grid_constant__ PolicyArgs A) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];      // > 48 KB: dynamic shared memory
+  MlpSmem& S = *reinterpret_cast<MlpSmem*>(smem_raw);
+  float (*tiles)[32 * kObs] = reinterpret_cast<float (*)[32 * kObs]>(smem_raw + sizeof(MlpSmem));
+  __shared__ unsigned long long blk_stats[3];
+  __shared__ double blk_ret;
+
+  load_mlp_smem(S, A.theta);
+  if (threadIdx.x < 3) blk_stats[threadIdx.x] = 0;
+  if (threadIdx.x == 3) blk_ret = 0.0;
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t warp_base = (int64_t)blockIdx.x * blockDim.x + warp * 32;
+  const int64_t i = warp_base + lane;
+  const bool active = i < A.n;
+  const int valid = (int)max((int64_t)0, min((int64_t)32, A.n - warp_base));
+  float* tile = tiles[warp];
+  const EnvParams& P = A.P;
+  const uint64_t env_id = P.env_offset + (uint64_t)i;
+  const int64_t n = A.n;
+
+  EnvState s = {};
+  if (active) s = load_state(A.state, i);
+
+  float std_[kAct], logstd_sum = 0.f;
+#pragma unroll
+  for (int o = 0; o < kAct; ++o) { std_[o] = expf(S.log_std[o]); logstd_sum += S.log_std[o]; }
+
+  uint32_t n_done = 0, n_term = 0, len_sum = 0;
+  float ret_sum = 0.f;
+  float4* p_act = A.actions + i;
+  float* p_logp = A.logp + i;
+  float* p_val = A.value + i;
+  float* p_rew = A.reward + i;
+  uint8_t* p_done = A.done + i;
+  float* p_obs = A.obs + warp_base * kObs;
+
+  for (int k = 0; k < A.K; ++k) {
+    float x[kObs];
+    write_obs<kObs>(x, s);
+    if (A.obs != nullptr && valid > 0) emit_obs_rows<kObs>(tile, p_obs, s, lane, valid, active);
+
+    float mean[kAct], val[1];
+    tower_forward<kAct>(S, 0, x, mean);
+    tower_forward<1>(S, 1, x, val);
+
+    float4 a;
+    float logp;
+    if (A.deterministic) {
+      a = make_float4(mean[0], mean[1], mean[2], mean[3]);
+      logp = -logstd_sum - kAct * kHalfLog2Pi;
+    } else {
+      const float4 z = noise_normals(P.seed, env_id, A.t0 + (uint64_t)k);
+      a = make_float4(fmaf(std_[0], z.x, mean[0]), fmaf(std_[1], z.y, mean[1]),
+                      fmaf(std_[2], z.z, mean[2]), fmaf(std_[3], z.w, mean[3]));
+      // Normal(mean, std).log_prob(a) summed over the 4 dims; (a - mean) / std == z up to rounding
+      logp = -0.5f * (z.x * z.x + z.y * z.y + z.z * z.z + z.w * z.w) - logstd_sum - kAct * kHalfLog2Pi;
+    }
+    // np.clip(a, low, high) for the env only (SB3 collect_rollouts); the buffer keeps `a`
+    const float4 f = make_float4(fminf(fmaxf(a.x, 0.f), P.motor_max), fminf(fmaxf(a.y, 0.f), P.motor_max),
+                                 fminf(fmaxf(a.z, 0.f), P.motor_max), fminf(fmaxf(a.w, 0.f), P.motor_max));
+    const StepResult r = step_env(s, P, f);
+    const bool done = r.crashed || r.timeout;
+    if (active) {
+      if (A.actions != nullptr) st_quad(p_act, a);
+      if (A.logp != nullptr) *p_logp = logp;
+      if (A.value != nullptr) *p_val = val[0];
+      if (A.reward != nullptr) *p_rew = r.reward;
+      if (A.done != nullptr) *p_done = done ? 1 : 0;
+      if (done) {
+        n_done += 1;
+        n_term += r.crashed ? 1 : 0;
+        len_sum += (uint32_t)s.ep_len;
+        ret_sum += s.ep_ret;
+        reset_env<RANDOMIZED>(s, P, env_id);       // the PPO path always auto-resets (DummyVecEnv)
+      }
+    }
+    p_act += n; p_logp += n; p_val += n; p_rew += n; p_done += n; p_obs += n * kObs;
+  }
+
+  // bootstrap value of the observation after the last step (SB3: policy.predict_values(new_obs))
+  {
+    float x[kObs], val[1];
+    write_obs<kObs>(x, s);
+    if (A.last_value != nullptr) {
+      tower_forward<1>(S, 1, x, val);
+      if (active) A.last_value[i] = val[0];
+    }
+    if (A.last_obs != nullptr && valid > 0)
+      emit_obs_rows<kObs>(tile, A.last_obs + warp_base * kObs, s, lane, valid, active);
+  }
+  if (active) store_state(A.state, i, s);
+
+  if (__ballot_sync(0xffffffffu, n_done != 0)) {
+    n_done = __reduce_add_sync(0xffffffffu, n_done);
+    n_term = __reduce_add_sync(0xffffffffu, n_term);
+    len_sum = __reduce_add_sync(0xffffffffu, len_sum);
+    double rs = (double)ret_sum;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, o);
+    if (lane == 0) {
+      atomicAdd(&blk_stats[0], (unsigned long long)n_done);
+      atomicAdd(&blk_stats[1], (unsigned long long)n_term);
+      atomicAdd(&blk_stats[2], (unsigned long long)len_sum);
+      atomicAdd(&blk_ret, rs);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && blk_stats[0] != 0) {
+    StatSlot* slot = A.stats + (blockIdx.x % kStatSlots);
+    atomicAdd(&slot->episodes, blk_stats[0]);
+    atomicAdd(&slot->terminated, blk_stats[1]);
+    atomicAdd(&slot->length_sum, blk_stats[2]);
+    atomicAdd(&slot->return_sum, blk_ret);
+  }
+}
+
+// policy(obs) for arbitrary observation rows: mean [B,4], value [B]  (PPO.predict / policy.forward)
+__global__ void __launch_bounds__(kPolBlock) policy_forward_kernel(const float* __restrict__ theta,
+                                                                   const float* __restrict__ obs, int64_t B,
+                                                                   float4* __restrict__ mean, float* __restrict__ value) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  MlpSmem& S = *reinterpret_cast<MlpSmem*>(smem_raw);
+  load_mlp_smem(S, theta);
+  __syncthreads();
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < B; r += (int64_t)gridDim.x * blockDim.x) {
+    float x[kObs], m[kAct], v[1];
+#pragma unroll
+    for (int i = 0; i < kObs; ++i) x[i] = obs[r * kObs + i];
+    tower_forward<kAct>(S, 0, x, m);
+    tower_forward<1>(S, 1, x, v);
+    if (mean) mean[r] = make_float4(m[0], m[1], m[2], m[3]);
+    if (value) value[r] = v[0];
+  }
+}
+
+// GAE(gamma, lambda) reverse scan, one env per thread (SB3 RolloutBuffer.compute_returns_and_advantage;
+// done[t] == episode_start[t+1]; no bootstrap on time-outs: the reference env sets no TimeLimit key).
+__global__ void gae_kernel(int K, int64_t n, const float* __restrict__ reward, const float* __restrict__ value,
+                           const uint8_t* __restrict__ done, const float* __restrict__ last_value, float gamma,
+                           float lam, float* __restrict__ adv, float* __restrict__ ret) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float next_v = last_value[i], last = 0.f;
+  for (int t = K - 1; t >= 0; --t) {
+    const int64_t j = (int64_t)t * n + i;
+    const float nnt = done[j] ? 0.f : 1.0f;
+    const float v = value[j];
+    const float delta = reward[j] + gamma * next_v * nnt - v;
+    last = delta + gamma * lam * nnt * last;
+    adv[j] = last;
+    ret[j] = last + v;
+    next_v = v;
+  }
+}
+
+}  // namespace dronecu

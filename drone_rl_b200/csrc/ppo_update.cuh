@@ -1,0 +1,437 @@
+// PPO minibatch update, float32 CUDA-core version: clipped-surrogate + value loss, forward and
+// backward through both towers, weight gradients, global-norm clip, Adam.  Restates what SB3's
+// PPO.train() does per minibatch (call site /root/reference/train.py:63-68) --
+// the source is not in /root/reference, parity is against oracle/ppo_oracle.py ("parity unpinned").
+//
+// Structure: a persistent grid (one CTA of 128 threads per SM) walks tiles of 128 samples.
+//   per tile, per tower:  thread-per-sample forward (weights as warp-broadcast LDS.128 from smem),
+//   loss gradient, thread-per-sample backward for the activations, and the three weight-gradient
+//   products (delta^T . activation, reduction over the 128 samples of the tile) as shared-memory
+//   register-tiled GEMMs.  Weight gradients accumulate in shared memory over the tiles of a CTA and
+//   leave as one partial vector per CTA; a second kernel sums the partials in a fixed order
+//   (deterministic, which the data-parallel equivalence test relies on); a third applies
+//   clip_grad_norm_ + Adam.
+#pragma once
+#include "ppo_rollout.cuh"
+
+namespace dronecu {
+
+constexpr int kUpdBlock = 128;          // threads == samples per tile
+constexpr int kRow = 68;                // row stride (floats) of the activation tiles: 16-byte aligned rows
+constexpr int kStats = 8;               // policy_loss, value_loss, approx_kl, clip_frac, count, spare...
+constexpr int kGradLen = kParams + kStats;
+
+struct UpdSmem {
+  MlpSmem fwd;                          // transposed weights for the forward pass
+  float W2[2][kHid][kHid];              // natural [out][in] for delta1 = delta2 . W2
+  float W3pi[kAct][kHid];               // natural for delta2 = g3 . W3
+  float G[kGradLen + 3];                // gradient + statistics accumulators of this CTA
+  float bufA[kUpdBlock][kRow];          // h1, later delta1
+  float bufB[kUpdBlock][kRow];          // h2, later delta2
+  float bufX[kUpdBlock][16];            // observation, x[15] = 1 (bias column)
+  float g3[kUpdBlock][kAct];            // head gradient per sample
+};
+
+struct UpdArgs {
+  const float* theta;        // [kParams]
+  const float* obs;          // [B,15]
+  const float4* actions;     // [B]
+  const float* old_logp;     // [B]
+  const float* adv;          // [B]
+  const float* ret;          // [B]
+  const int32_t* index;      // [m] rows of this minibatch (nullptr: rows first .. first+m)
+  int64_t first, m;
+  float adv_mean, adv_inv_std;   // (adv - mean) * inv_std ; (0, 1) disables normalisation
+  const double* adv_stats;       // nullable: [sum, sum of squares, count] -> overrides the two scalars
+  float clip, vf_coef, ent_coef;
+  float* partials;           // [gridDim.x, kGradLen]
+};
+
+// forward of one tower keeping what the backward pass needs: h1 -> bufA row, h2 -> bufB row
+template <int NOUT>
+__device__ __forceinline__ void tower_forward_keep(const MlpSmem& S, const int t, const float (&x)[kObs],
+                                                   float* rowA, float* rowB, float (&out)[NOUT]) {
+  float h1[kHid];
+#pragma unroll
+  for (int q = 0; q < kHid / 4; ++q) {
+    const float4 b = reinterpret_cast<const float4*>(S.b1[t])[q];
+    h1[4 * q] = b.x; h1[4 * q + 1] = b.y; h1[4 * q + 2] = b.z; h1[4 * q + 3] = b.w;
+  }
+#pragma unroll
+  for (int i = 0; i < kObs; ++i) {
+    const float xi = x[i];
+#pragma unroll
+    for (int q = 0; q < kHid / 4; ++q) {
+      const float4 w = reinterpret_cast<const float4*>(S.W1T[t][i])[q];
+      h1[4 * q] = fmaf(w.x, xi, h1[4 * q]); h1[4 * q + 1] = fmaf(w.y, xi, h1[4 * q + 1]);
+      h1[4 * q + 2] = fmaf(w.z, xi, h1[4 * q + 2]); h1[4 * q + 3] = fmaf(w.w, xi, h1[4 * q + 3]);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < kHid / 4; ++q) {
+    float4 v;
+    v.x = h1[4 * q] = tanh_fast(h1[4 * q]); v.y = h1[4 * q + 1] = tanh_fast(h1[4 * q + 1]);
+    v.z = h1[4 * q + 2] = tanh_fast(h1[4 * q + 2]); v.w = h1[4 * q + 3] = tanh_fast(h1[4 * q + 3]);
+    reinterpret_cast<float4*>(rowA)[q] = v;
+  }
+  if constexpr (NOUT == kAct) {
+#pragma unroll
+    for (int o = 0; o < kAct; ++o) out[o] = S.b3pi[o];
+  } else {
+    out[0] = S.b3vf;
+  }
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    float acc[16];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 b = reinterpret_cast<const float4*>(S.b2[t] + 16 * c)[q];
+      acc[4 * q] = b.x; acc[4 * q + 1] = b.y; acc[4 * q + 2] = b.z; acc[4 * q + 3] = b.w;
+    }
+#pragma unroll
+    for (int i = 0; i < kHid; ++i) {
+      const float hi = h1[i];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 w = reinterpret_cast<const float4*>(S.W2T[t][i] + 16 * c)[q];
+        acc[4 * q] = fmaf(w.x, hi, acc[4 * q]); acc[4 * q + 1] = fmaf(w.y, hi, acc[4 * q + 1]);
+        acc[4 * q + 2] = fmaf(w.z, hi, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(w.w, hi, acc[4 * q + 3]);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float4 v;
+      v.x = tanh_fast(acc[4 * q]); v.y = tanh_fast(acc[4 * q + 1]);
+      v.z = tanh_fast(acc[4 * q + 2]); v.w = tanh_fast(acc[4 * q + 3]);
+      reinterpret_cast<float4*>(rowB + 16 * c)[q] = v;
+      const float a4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int j = 16 * c + 4 * q + e;
+        if constexpr (NOUT == kAct) {
+          const float4 w = reinterpret_cast<const float4*>(S.W3piT[j])[0];
+          out[0] = fmaf(w.x, a4[e], out[0]); out[1] = fmaf(w.y, a4[e], out[1]);
+          out[2] = fmaf(w.z, a4[e], out[2]); out[3] = fmaf(w.w, a4[e], out[3]);
+        } else {
+          out[0] = fmaf(S.W3vf[j], a4[e], out[0]);
+        }
+      }
+    }
+  }
+}
+
+// backward of one tower for the thread's own sample.  On entry rowB = h2, rowA = h1, g3 = dL/d(out).
+// Leaves delta2 in rowB and returns delta1 (still to be written over rowA by the caller once the
+// dW2 product has consumed h1).
+template <int NOUT>
+__device__ __forceinline__ void tower_backward(const UpdSmem& U, const int t, const float (&g3)[NOUT],
+                                               const float* rowA, float* rowB, float (&d1)[kHid]) {
+#pragma unroll
+  for (int i = 0; i < kHid; ++i) d1[i] = 0.f;
+#pragma unroll
+  for (int q = 0; q < kHid / 4; ++q) {
+    const float4 h = reinterpret_cast<const float4*>(rowB)[q];
+    const float h4[4] = {h.x, h.y, h.z, h.w};
+    float d4[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int j = 4 * q + e;
+      float up;
+      if constexpr (NOUT == kAct) {
+        up = g3[0] * U.W3pi[0][j] + g3[1] * U.W3pi[1][j] + g3[2] * U.W3pi[2][j] + g3[3] * U.W3pi[3][j];
+      } else {
+        up = g3[0] * U.fwd.W3vf[j];
+      }
+      d4[e] = up * (1.0f - h4[e] * h4[e]);                      // tanh'
+      const float dj = d4[e];
+#pragma unroll
+      for (int qq = 0; qq < kHid / 4; ++qq) {
+        const float4 w = reinterpret_cast<const float4*>(U.W2[t][j])[qq];
+        d1[4 * qq] = fmaf(w.x, dj, d1[4 * qq]); d1[4 * qq + 1] = fmaf(w.y, dj, d1[4 * qq + 1]);
+        d1[4 * qq + 2] = fmaf(w.z, dj, d1[4 * qq + 2]); d1[4 * qq + 3] = fmaf(w.w, dj, d1[4 * qq + 3]);
+      }
+    }
+    reinterpret_cast<float4*>(rowB)[q] = make_float4(d4[0], d4[1], d4[2], d4[3]);
+  }
+#pragma unroll
+  for (int q = 0; q < kHid / 4; ++q) {
+    const float4 h = reinterpret_cast<const float4*>(rowA)[q];
+    d1[4 * q] *= 1.0f - h.x * h.x; d1[4 * q + 1] *= 1.0f - h.y * h.y;
+    d1[4 * q + 2] *= 1.0f - h.z * h.z; d1[4 * q + 3] *= 1.0f - h.w * h.w;
+  }
+}
+
+// G[w2off + j*64 + i] += sum_s bufB[s][j] * bufA[s][i]   (64 x 64 outputs, 128 threads x (4 j x 8 i))
+// G[b2off + j]        += sum_s bufB[s][j]
+__device__ __forceinline__ void wgrad_hidden(UpdSmem& U, int w2off, int b2off, int rows) {
+  const int jt = threadIdx.x >> 3, it = threadIdx.x & 7;
+  float acc[4][8];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 8; ++b) acc[a][b] = 0.f;
+  for (int s = 0; s < rows; ++s) {
+    const float4 d = reinterpret_cast<const float4*>(U.bufB[s])[jt];
+    const float4 h0 = reinterpret_cast<const float4*>(U.bufA[s])[it];
+    const float4 h1 = reinterpret_cast<const float4*>(U.bufA[s])[8 + it];
+    const float dd[4] = {d.x, d.y, d.z, d.w};
+    const float hh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 8; ++b) acc[a][b] = fmaf(dd[a], hh[b], acc[a][b]);
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      const int j = 4 * jt + a, i = (b < 4) ? (4 * it + b) : (32 + 4 * it + (b - 4));
+      U.G[w2off + j * kHid + i] += acc[a][b];
+    }
+  if (threadIdx.x < kHid) {
+    float sum = 0.f;
+    for (int s = 0; s < rows; ++s) sum += U.bufB[s][threadIdx.x];
+    U.G[b2off + threadIdx.x] += sum;
+  }
+}
+
+// G[w1off + j*15 + i] += sum_s bufA[s][j] * bufX[s][i] (i < 15);  G[b1off + j] += sum_s bufA[s][j] * 1
+__device__ __forceinline__ void wgrad_input(UpdSmem& U, int w1off, int b1off, int rows) {
+  const int jt = threadIdx.x >> 2, it = threadIdx.x & 3;     // j = 2 jt + {0,1}, i = 4 it + {0..3}
+  float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  for (int s = 0; s < rows; ++s) {
+    const float2 d = reinterpret_cast<const float2*>(U.bufA[s])[jt];
+    const float4 x = reinterpret_cast<const float4*>(U.bufX[s])[it];
+    acc[0][0] = fmaf(d.x, x.x, acc[0][0]); acc[0][1] = fmaf(d.x, x.y, acc[0][1]);
+    acc[0][2] = fmaf(d.x, x.z, acc[0][2]); acc[0][3] = fmaf(d.x, x.w, acc[0][3]);
+    acc[1][0] = fmaf(d.y, x.x, acc[1][0]); acc[1][1] = fmaf(d.y, x.y, acc[1][1]);
+    acc[1][2] = fmaf(d.y, x.z, acc[1][2]); acc[1][3] = fmaf(d.y, x.w, acc[1][3]);
+  }
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int j = 2 * jt + a, i = 4 * it + b;
+      if (i < kObs) U.G[w1off + j * kObs + i] += acc[a][b];
+      else U.G[b1off + j] += acc[a][b];
+    }
+}
+
+// head: G[w3off + o*64 + j] += sum_s g3[s][o] * bufB[s][j] ;  G[b3off + o] += sum_s g3[s][o]
+template <int NOUT>
+__device__ __forceinline__ void wgrad_head(UpdSmem& U, int w3off, int b3off, int rows) {
+  for (int idx = threadIdx.x; idx < NOUT * kHid; idx += kUpdBlock) {
+    const int o = idx / kHid, j = idx % kHid;
+    float sum = 0.f;
+    for (int s = 0; s < rows; ++s) sum = fmaf(U.g3[s][o], U.bufB[s][j], sum);
+    U.G[w3off + idx] += sum;
+  }
+  if (threadIdx.x < NOUT) {
+    float sum = 0.f;
+    for (int s = 0; s < rows; ++s) sum += U.g3[s][threadIdx.x];
+    U.G[b3off + threadIdx.x] += sum;
+  }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(kUpdBlock, 1) ppo_grad_kernel(const __grid_constant__ UpdArgs A) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  UpdSmem& U = *reinterpret_cast<UpdSmem*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31;
+
+  load_mlp_smem(U.fwd, A.theta);
+  for (int idx = tid; idx < 2 * kHid * kHid; idx += kUpdBlock) {
+    const int t = idx / (kHid * kHid), q = idx % (kHid * kHid);
+    U.W2[t][q / kHid][q % kHid] = A.theta[(t ? O_VF_W2 : O_PI_W2) + q];
+  }
+  for (int idx = tid; idx < kAct * kHid; idx += kUpdBlock) U.W3pi[idx / kHid][idx % kHid] = A.theta[O_PI_W3 + idx];
+  for (int idx = tid; idx < kGradLen + 3; idx += kUpdBlock) U.G[idx] = 0.f;
+  __syncthreads();
+
+  float std_inv[kAct], logstd_sum = 0.f;
+#pragma unroll
+  for (int o = 0; o < kAct; ++o) { std_inv[o] = expf(-U.fwd.log_std[o]); logstd_sum += U.fwd.log_std[o]; }
+  float adv_mean = A.adv_mean, adv_inv_std = A.adv_inv_std;
+  if (A.adv_stats != nullptr) {        // SB3: (adv - adv.mean()) / (adv.std() + 1e-8), torch.std is unbiased
+    const double cnt = A.adv_stats[2], mu = A.adv_stats[0] / cnt;
+    const double var = (A.adv_stats[1] - A.adv_stats[0] * mu) / (cnt - 1.0);
+    adv_mean = (float)mu;
+    adv_inv_std = (float)(1.0 / (sqrt(fmax(var, 0.0)) + 1e-8));
+  }
+
+  const int64_t n_tiles = (A.m + kUpdBlock - 1) / kUpdBlock;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t pos = tile * kUpdBlock + tid;
+    const bool live = pos < A.m;
+    const int rows = (int)min((int64_t)kUpdBlock, A.m - tile * kUpdBlock);
+    const int64_t row = live ? (A.index ? (int64_t)A.index[pos] : A.first + pos) : 0;
+
+    float x[kObs];
+#pragma unroll
+    for (int i = 0; i < kObs; ++i) x[i] = live ? A.obs[row * kObs + i] : 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      reinterpret_cast<float4*>(U.bufX[tid])[q] =
+          make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], (q == 3) ? 1.0f : x[4 * q + 3]);
+
+    // ---------------- policy tower ----------------
+    float mean[kAct];
+    tower_forward_keep<kAct>(U.fwd, 0, x, U.bufA[tid], U.bufB[tid], mean);
+    float g_pi[kAct] = {0.f, 0.f, 0.f, 0.f}, g_ls[kAct] = {0.f, 0.f, 0.f, 0.f};
+    float st_pl = 0.f, st_kl = 0.f, st_cf = 0.f;
+    if (live) {
+      const float4 a = A.actions[row];
+      const float av[4] = {a.x, a.y, a.z, a.w};
+      float z[kAct], sq = 0.f;
+#pragma unroll
+      for (int o = 0; o < kAct; ++o) { z[o] = (av[o] - mean[o]) * std_inv[o]; sq = fmaf(z[o], z[o], sq); }
+      const float logp = -0.5f * sq - logstd_sum - kAct * kHalfLog2Pi;
+      const float log_ratio = logp - A.old_logp[row];
+      const float ratio = expf(log_ratio);
+      const float adv = (A.adv[row] - adv_mean) * adv_inv_std;
+      const float lo = 1.0f - A.clip, hi = 1.0f + A.clip;
+      const float s1 = adv * ratio, s2 = adv * fminf(fmaxf(ratio, lo), hi);
+      const bool inside = (ratio >= lo) && (ratio <= hi);
+      const float dl_dlogp = (inside || s1 < s2) ? -adv * ratio : 0.f;     // d(-min(s1,s2)) / d logp
+#pragma unroll
+      for (int o = 0; o < kAct; ++o) {
+        g_pi[o] = dl_dlogp * z[o] * std_inv[o];
+        g_ls[o] = dl_dlogp * (z[o] * z[o] - 1.0f) - A.ent_coef;
+      }
+      st_pl = -fminf(s1, s2);
+      st_kl = (ratio - 1.0f) - log_ratio;
+      st_cf = (fabsf(ratio - 1.0f) > A.clip) ? 1.0f : 0.f;
+    }
+    reinterpret_cast<float4*>(U.g3[tid])[0] = make_float4(g_pi[0], g_pi[1], g_pi[2], g_pi[3]);
+    // log_std gradient + statistics: warp sums, one shared-memory atomic per warp
+    {
+      float v[7] = {g_ls[0], g_ls[1], g_ls[2], g_ls[3], st_pl, st_kl, st_cf};
+#pragma unroll
+      for (int q = 0; q < 7; ++q) v[q] = warp_sum(v[q]);
+      if (lane == 0) {
+#pragma unroll
+        for (int o = 0; o < kAct; ++o) atomicAdd(&U.G[O_LOGSTD + o], v[o]);
+        atomicAdd(&U.G[kParams + 0], v[4]);
+        atomicAdd(&U.G[kParams + 2], v[5]);
+        atomicAdd(&U.G[kParams + 3], v[6]);
+      }
+    }
+    __syncthreads();                                   // h2 (bufB), g3 complete for the whole tile
+    wgrad_head<kAct>(U, O_PI_W3, O_PI_B3, rows);
+    __syncthreads();                                   // dW3 has consumed h2
+    float d1[kHid];
+    tower_backward<kAct>(U, 0, g_pi, U.bufA[tid], U.bufB[tid], d1);
+    __syncthreads();                                   // delta2 rows complete
+    wgrad_hidden(U, O_PI_W2, O_PI_B2, rows);
+    __syncthreads();                                   // dW2 has consumed h1
+#pragma unroll
+    for (int q = 0; q < kHid / 4; ++q)
+      reinterpret_cast<float4*>(U.bufA[tid])[q] = make_float4(d1[4 * q], d1[4 * q + 1], d1[4 * q + 2], d1[4 * q + 3]);
+    __syncthreads();
+    wgrad_input(U, O_PI_W1, O_PI_B1, rows);
+    __syncthreads();
+
+    // ---------------- value tower ----------------
+    float val[1];
+    tower_forward_keep<1>(U.fwd, 1, x, U.bufA[tid], U.bufB[tid], val);
+    float g_v[1] = {0.f}, st_vl = 0.f;
+    if (live) {
+      const float diff = val[0] - A.ret[row];
+      g_v[0] = 2.0f * A.vf_coef * diff;                 // d(vf_coef * (ret - v)^2) / dv
+      st_vl = diff * diff;
+    }
+    U.g3[tid][0] = g_v[0];
+    {
+      const float v0 = warp_sum(st_vl), v1 = warp_sum(live ? 1.0f : 0.f);
+      if (lane == 0) { atomicAdd(&U.G[kParams + 1], v0); atomicAdd(&U.G[kParams + 4], v1); }
+    }
+    __syncthreads();
+    wgrad_head<1>(U, O_VF_W3, O_VF_B3, rows);
+    __syncthreads();
+    tower_backward<1>(U, 1, g_v, U.bufA[tid], U.bufB[tid], d1);
+    __syncthreads();
+    wgrad_hidden(U, O_VF_W2, O_VF_B2, rows);
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < kHid / 4; ++q)
+      reinterpret_cast<float4*>(U.bufA[tid])[q] = make_float4(d1[4 * q], d1[4 * q + 1], d1[4 * q + 2], d1[4 * q + 3]);
+    __syncthreads();
+    wgrad_input(U, O_VF_W1, O_VF_B1, rows);
+    __syncthreads();
+  }
+
+  float* out = A.partials + (size_t)blockIdx.x * kGradLen;
+  for (int idx = tid; idx < kGradLen; idx += kUpdBlock) out[idx] = U.G[idx];
+}
+
+// fixed-order sum of the per-CTA partial vectors -> grad[kGradLen] (sum over samples, not yet / M)
+__global__ void ppo_reduce_kernel(const float* __restrict__ partials, int n_partials, float* __restrict__ grad) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= kGradLen) return;
+  float sum = 0.f;
+  for (int p = 0; p < n_partials; ++p) sum += partials[(size_t)p * kGradLen + idx];
+  grad[idx] = sum;
+}
+
+// advantage statistics of a minibatch: out[0] += sum, out[1] += sum of squares, out[2] += count
+__global__ void adv_stats_kernel(const float* __restrict__ adv, const int32_t* __restrict__ index, int64_t first,
+                                 int64_t m, double* __restrict__ out) {
+  double s = 0.0, q = 0.0;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < m; p += (int64_t)gridDim.x * blockDim.x) {
+    const double a = (double)adv[index ? (int64_t)index[p] : first + p];
+    s += a; q += a * a;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(&out[0], s); atomicAdd(&out[1], q); }
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&out[2], (double)m);
+}
+
+struct AdamArgs {
+  float* theta; const float* grad; float* m; float* v;
+  float inv_count;           // 1 / (global number of samples in the minibatch)
+  float lr_over_bc1, inv_sqrt_bc2, beta1, beta2, eps, max_norm;
+  float* info;               // [kStats + 1]: mean statistics + pre-clip gradient norm
+};
+
+// torch.nn.utils.clip_grad_norm_(max_norm) + torch.optim.Adam.step() on the flat vector (one CTA)
+__global__ void __launch_bounds__(1024) ppo_apply_kernel(const AdamArgs A) {
+  __shared__ float red[32];
+  __shared__ float coef_s;
+  float sq = 0.f;
+  for (int i = threadIdx.x; i < kParams; i += blockDim.x) {
+    const float g = A.grad[i] * A.inv_count;
+    sq = fmaf(g, g, sq);
+  }
+  sq = warp_sum(sq);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sq;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) {
+      const float norm = sqrtf(v);
+      coef_s = fminf(A.max_norm / (norm + 1e-6f), 1.0f);
+      if (A.info) {
+        for (int q = 0; q < kStats; ++q) A.info[q] = A.grad[kParams + q] * (q == 4 ? 1.0f : A.inv_count);
+        A.info[kStats] = norm;
+      }
+    }
+  }
+  __syncthreads();
+  const float coef = coef_s * A.inv_count;
+  for (int i = threadIdx.x; i < kParams; i += blockDim.x) {
+    const float g = A.grad[i] * coef;
+    const float m = A.beta1 * A.m[i] + (1.0f - A.beta1) * g;
+    const float v = A.beta2 * A.v[i] + (1.0f - A.beta2) * g * g;
+    A.m[i] = m; A.v[i] = v;
+    A.theta[i] -= A.lr_over_bc1 * m / (sqrtf(v) * A.inv_sqrt_bc2 + A.eps);
+  }
+}
+
+}  // namespace dronecu

@@ -1,0 +1,271 @@
+"""PPO on the GPU: the rollout + update hot path of ``PPO("MlpPolicy", env)`` (reference
+train.py:36-43, :63-68) with SB3's defaults, computed by the CUDA kernels behind the C ABI.
+
+Host side only orchestrates: ONE launch collects ``n_steps`` env steps for every env with the policy
+evaluated in-kernel (``dronecu_rollout_policy``), one computes GAE, and each minibatch is
+adv-stats -> grad -> [NCCL all-reduce] -> clip+Adam.  torch supplies device memory, the random
+permutation and ``torch.distributed``; no torch op touches the numerics.
+
+Data parallel (``torch.distributed`` initialised, one process per GPU): every rank owns a contiguous
+shard of global env ids and its own rollout buffers; per optimiser step the flat gradient (10,705
+float32 incl. statistics) and the three advantage sums are all-reduced, so the update equals the
+single-GPU update over the union of the shards.
+
+PARITY UNPINNED: SB3 is not in the reference tree; tests compare against oracle/ppo_oracle.py.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import time
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import GRAD_LEN, POLICY_PARAMS, PolicyOut, PPOConfig
+from .core import DroneBatch, EnvConfig, _ptr, _stream_ptr
+
+_SHAPES = [("pi.W1", (64, 15)), ("pi.b1", (64,)), ("pi.W2", (64, 64)), ("pi.b2", (64,)), ("pi.W3", (4, 64)),
+           ("pi.b3", (4,)), ("vf.W1", (64, 15)), ("vf.b1", (64,)), ("vf.W2", (64, 64)), ("vf.b2", (64,)),
+           ("vf.W3", (1, 64)), ("vf.b3", (1,)), ("log_std", (4,))]
+# names of the same tensors in an SB3 ActorCriticPolicy state_dict (for zip import / export)
+SB3_NAMES = {"pi.W1": "mlp_extractor.policy_net.0.weight", "pi.b1": "mlp_extractor.policy_net.0.bias",
+             "pi.W2": "mlp_extractor.policy_net.2.weight", "pi.b2": "mlp_extractor.policy_net.2.bias",
+             "pi.W3": "action_net.weight", "pi.b3": "action_net.bias",
+             "vf.W1": "mlp_extractor.value_net.0.weight", "vf.b1": "mlp_extractor.value_net.0.bias",
+             "vf.W2": "mlp_extractor.value_net.2.weight", "vf.b2": "mlp_extractor.value_net.2.bias",
+             "vf.W3": "value_net.weight", "vf.b3": "value_net.bias", "log_std": "log_std"}
+
+
+def init_policy_params(seed: int = 0) -> torch.Tensor:
+    """SB3 ActorCriticPolicy initialisation: orthogonal weights (gain sqrt2 towers, 0.01 action head,
+    1 value head), zero biases, log_std = 0.  Flat float32 CPU vector [10697]."""
+    g = torch.Generator().manual_seed(seed)
+    gains = {"pi.W1": math.sqrt(2), "pi.W2": math.sqrt(2), "pi.W3": 0.01,
+             "vf.W1": math.sqrt(2), "vf.W2": math.sqrt(2), "vf.W3": 1.0}
+    flat, off = torch.zeros(POLICY_PARAMS, dtype=torch.float64), 0
+    for name, shape in _SHAPES:
+        n = int(np.prod(shape))
+        if name in gains:
+            rows, cols = shape
+            a = torch.randn((max(rows, cols), min(rows, cols)), generator=g, dtype=torch.float64)
+            q, r = torch.linalg.qr(a)
+            q = q * torch.sign(torch.diag(r))
+            if rows < cols:
+                q = q.t()
+            flat[off:off + n] = (q[:rows, :cols] * gains[name]).reshape(-1)
+        off += n
+    return flat.to(torch.float32)
+
+
+def unpack_params(flat: torch.Tensor) -> dict:
+    out, off = {}, 0
+    for name, shape in _SHAPES:
+        n = int(np.prod(shape))
+        out[name] = flat[off:off + n].reshape(shape)
+        off += n
+    return out
+
+
+class RolloutBuffers:
+    """Device-resident rollout buffers [K, n, ...] (SB3 RolloutBuffer)."""
+
+    def __init__(self, K, n, device):
+        f = dict(dtype=torch.float32, device=device)
+        self.obs = torch.empty(K, n, 15, **f)
+        self.actions = torch.empty(K, n, 4, **f)
+        self.logp = torch.empty(K, n, **f)
+        self.value = torch.empty(K, n, **f)
+        self.reward = torch.empty(K, n, **f)
+        self.done = torch.empty(K, n, dtype=torch.uint8, device=device)
+        self.last_value = torch.empty(n, **f)
+        self.adv = torch.empty(K, n, **f)
+        self.ret = torch.empty(K, n, **f)
+
+
+class PPO:
+    """SB3-shaped trainer: ``PPO(env).learn(total_timesteps)``, ``predict``, ``save`` / ``load``.
+
+    ``env`` is a ``DroneBatch`` (or anything with a ``.batch`` DroneBatch, e.g. ``DroneVecEnv``), or an
+    int = number of envs to create.  Defaults are SB3's (n_steps 2048, batch_size 64, n_epochs 10,
+    gamma 0.99, gae_lambda 0.95, clip 0.2, ent 0, vf 0.5, max_grad_norm 0.5, lr 3e-4, Adam eps 1e-5).
+    ``batch_size`` counts samples PER RANK.
+    """
+
+    def __init__(self, env=1, n_steps: int = 2048, batch_size: int = 64, n_epochs: int = 10, gamma: float = 0.99,
+                 gae_lambda: float = 0.95, clip_range: float = 0.2, ent_coef: float = 0.0, vf_coef: float = 0.5,
+                 max_grad_norm: float = 0.5, learning_rate: float = 3e-4, normalize_advantage: bool = True,
+                 seed: int = 0, device: int = 0, verbose: int = 0, policy_seed: Optional[int] = None):
+        self.lib = _lib.load()
+        self.rank, self.world = 0, 1
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            self.rank, self.world = torch.distributed.get_rank(), torch.distributed.get_world_size()
+        if isinstance(env, int):
+            env = DroneBatch(env, EnvConfig.single(), device=device, seed=seed, env_offset=self.rank * env)
+        self.batch: DroneBatch = getattr(env, "batch", env)
+        if self.batch.obs_dim != 15 or not self.batch.config.auto_reset:
+            raise ValueError("PPO needs the DroneGymEnv spec (15-dim obs) with auto-reset")
+        self.device = self.batch.device
+        self.n_envs, self.n_steps, self.batch_size, self.n_epochs = self.batch.n, n_steps, batch_size, n_epochs
+        self.gamma, self.gae_lambda, self.normalize_advantage = gamma, gae_lambda, normalize_advantage
+        self.verbose, self.seed = verbose, seed
+        cfg = PPOConfig()
+        self.lib.dronecu_ppo_config_default(C.byref(cfg))
+        cfg.learning_rate, cfg.clip_range, cfg.ent_coef = learning_rate, clip_range, ent_coef
+        cfg.vf_coef, cfg.max_grad_norm = vf_coef, max_grad_norm
+        self.cfg = cfg
+        h = C.c_void_p()
+        _lib.check(self.lib.dronecu_ppo_create(C.byref(cfg), self.device.index, C.byref(h)), "dronecu_ppo_create")
+        self._h = h
+        self.params = init_policy_params(seed if policy_seed is None else policy_seed).to(self.device)
+        self.buf = RolloutBuffers(n_steps, self.n_envs, self.device)
+        self._grad = torch.zeros(GRAD_LEN, dtype=torch.float32, device=self.device)
+        self._adv_stats = torch.zeros(3, dtype=torch.float64, device=self.device)
+        self._info = torch.zeros(9, dtype=torch.float32, device=self.device)
+        self._gen = torch.Generator(device=self.device).manual_seed(seed + 1)
+        self.num_timesteps, self.n_updates = 0, 0
+        self.logger_values: dict = {}
+        self.launches = 0
+        self.batch.reset()          # SB3 _setup_learn: env.reset()  (ep_num 1 -> 2)
+
+    # -- lifetime ------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.dronecu_ppo_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- rollout ------------------------------------------------------------------------------------
+    def collect_rollouts(self, deterministic: bool = False):
+        """One launch: n_steps env steps for every env, policy evaluated in-kernel; then GAE."""
+        b, K, n = self.buf, self.n_steps, self.n_envs
+        out = PolicyOut(b.obs.data_ptr(), b.actions.data_ptr(), b.logp.data_ptr(), b.value.data_ptr(),
+                        b.reward.data_ptr(), b.done.data_ptr(), b.last_value.data_ptr(), None)
+        st = _stream_ptr(self.device)
+        _lib.check(self.lib.dronecu_rollout_policy(self.batch._h, K, _ptr(self.params), int(deterministic),
+                                                   C.byref(out), st), "dronecu_rollout_policy")
+        _lib.check(self.lib.dronecu_gae(self.device.index, K, n, _ptr(b.reward), _ptr(b.value), _ptr(b.done),
+                                        _ptr(b.last_value), self.gamma, self.gae_lambda, _ptr(b.adv), _ptr(b.ret), st),
+                   "dronecu_gae")
+        self.launches += 2
+        self.num_timesteps += K * n * self.world
+
+    # -- update -------------------------------------------------------------------------------------
+    def _minibatch(self, index: Optional[torch.Tensor], first: int, m: int):
+        b, st = self.buf, _stream_ptr(self.device)
+        stats_ptr = None
+        if self.normalize_advantage:
+            self._adv_stats.zero_()
+            _lib.check(self.lib.dronecu_ppo_adv_stats(self._h, _ptr(b.adv), _ptr(index), first, m,
+                                                      _ptr(self._adv_stats), st), "dronecu_ppo_adv_stats")
+            if self.world > 1:
+                torch.distributed.all_reduce(self._adv_stats)
+            stats_ptr = _ptr(self._adv_stats)
+            self.launches += 2
+        _lib.check(self.lib.dronecu_ppo_grad(self._h, _ptr(self.params), _ptr(b.obs), _ptr(b.actions), _ptr(b.logp),
+                                             _ptr(b.adv), _ptr(b.ret), _ptr(index), first, m, 0.0, 1.0, stats_ptr,
+                                             _ptr(self._grad), st), "dronecu_ppo_grad")
+        if self.world > 1:
+            torch.distributed.all_reduce(self._grad)      # NCCL: 42.8 KB, the only collective of the data path
+        _lib.check(self.lib.dronecu_ppo_apply(self._h, _ptr(self.params), _ptr(self._grad),
+                                              1.0 / (m * self.world), _ptr(self._info), st), "dronecu_ppo_apply")
+        self.launches += 3
+        self.n_updates += 1
+
+    def train(self):
+        """SB3 PPO.train(): n_epochs passes over the buffer in random minibatches of batch_size."""
+        B = self.n_steps * self.n_envs
+        for _ in range(self.n_epochs):
+            perm = torch.randperm(B, device=self.device, generator=self._gen, dtype=torch.int64).to(torch.int32)
+            for start in range(0, B, self.batch_size):
+                m = min(self.batch_size, B - start)
+                self._minibatch(perm[start:start + m], 0, m)
+        info = self._info.cpu().numpy()
+        self.logger_values.update({"train/policy_gradient_loss": float(info[0]), "train/value_loss": float(info[1]),
+                                   "train/approx_kl": float(info[2]), "train/clip_fraction": float(info[3]),
+                                   "train/loss": float(info[0] + self.cfg.vf_coef * info[1]),
+                                   "train/grad_norm": float(info[8]), "train/n_updates": self.n_updates,
+                                   "train/std": float(torch.exp(self.params[-4:]).mean())})
+
+    def learn(self, total_timesteps: int, log_interval: int = 1, callback=None):
+        t0, it = time.time(), 0
+        while self.num_timesteps < total_timesteps:
+            self.collect_rollouts()
+            st = self.batch.episode_stats(reset=True)
+            if self.world > 1:
+                v = torch.tensor([st["return_sum"], float(st["length_sum"]), float(st["episodes"])],
+                                 dtype=torch.float64, device=self.device)
+                torch.distributed.all_reduce(v)
+                st["ep_rew_mean"] = float(v[0] / v[2]) if v[2] > 0 else float("nan")
+                st["ep_len_mean"] = float(v[1] / v[2]) if v[2] > 0 else float("nan")
+            self.train()
+            it += 1
+            self.logger_values.update({"rollout/ep_rew_mean": st["ep_rew_mean"], "rollout/ep_len_mean": st["ep_len_mean"],
+                                       "time/iterations": it, "time/total_timesteps": self.num_timesteps,
+                                       "time/fps": int(self.num_timesteps / max(time.time() - t0, 1e-9))})
+            if callback is not None and callback(self) is False:
+                break
+            if self.verbose and self.rank == 0 and it % log_interval == 0:
+                print(" | ".join(f"{k}={v:.4g}" if isinstance(v, float) else f"{k}={v}"
+                                 for k, v in self.logger_values.items()), flush=True)
+        return self
+
+    # -- inference ----------------------------------------------------------------------------------
+    def policy_forward(self, obs: torch.Tensor):
+        """(mean [B,4], value [B]) for device observations [B,15]."""
+        obs = obs.to(self.device, torch.float32).contiguous()
+        B = obs.shape[0]
+        mean = torch.empty(B, 4, dtype=torch.float32, device=self.device)
+        value = torch.empty(B, dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.dronecu_policy_forward(self.device.index, B, _ptr(self.params), _ptr(obs), _ptr(mean),
+                                                   _ptr(value), _stream_ptr(self.device)), "dronecu_policy_forward")
+        return mean, value
+
+    def predict(self, observation, state=None, episode_start=None, deterministic: bool = False):
+        """SB3 ``predict``: numpy obs [15] or [n,15] -> (clipped action, None)  (train.py:48, test.py:14)."""
+        obs = np.asarray(observation, dtype=np.float32)
+        single = obs.ndim == 1
+        mean, _ = self.policy_forward(torch.from_numpy(obs.reshape(-1, 15)))
+        if not deterministic:
+            std = torch.exp(self.params[-4:])
+            mean = mean + std * torch.randn(mean.shape, device=self.device, generator=self._gen)
+        act = torch.clamp(mean, 0.0, self.batch.config.motor_max).cpu().numpy()
+        return (act[0] if single else act), None
+
+    # -- checkpoint (policy + Adam + env curriculum / RNG state; the reference loses the env state) ------
+    def state_dict(self) -> dict:
+        mom = torch.empty(2 * POLICY_PARAMS, dtype=torch.float32, device=self.device)
+        step = C.c_int64()
+        _lib.check(self.lib.dronecu_ppo_get_state(self._h, _ptr(mom), C.byref(step), _stream_ptr(self.device)))
+        torch.cuda.synchronize(self.device)
+        return {"params": self.params.cpu(), "adam": mom.cpu(), "adam_step": step.value,
+                "num_timesteps": self.num_timesteps, "n_updates": self.n_updates,
+                "env_state": self.batch.get_state(), "env_global_step": self.batch.global_step,
+                "sb3_policy": {SB3_NAMES[k]: v.clone() for k, v in unpack_params(self.params.cpu()).items()}}
+
+    def load_state_dict(self, sd: dict, load_env: bool = True):
+        self.params.copy_(sd["params"].to(self.device))
+        _lib.check(self.lib.dronecu_ppo_set_state(self._h, _ptr(sd["adam"].to(self.device)), int(sd["adam_step"]),
+                                                  _stream_ptr(self.device)))
+        torch.cuda.synchronize(self.device)
+        self.num_timesteps, self.n_updates = sd["num_timesteps"], sd["n_updates"]
+        if load_env and "env_state" in sd and sd["env_state"]["pos"].shape[0] == self.n_envs:
+            self.batch.set_state(**sd["env_state"])
+            self.batch.global_step = sd.get("env_global_step", self.batch.global_step)
+
+    def save(self, path: str):
+        torch.save(self.state_dict(), path if path.endswith((".pt", ".zip")) else path + ".pt")
+
+    @classmethod
+    def load(cls, path: str, env=1, **kw):
+        sd = torch.load(path, weights_only=False)
+        model = cls(env, **kw)
+        model.load_state_dict(sd)
+        return model

@@ -141,6 +141,7 @@ int dronecu_destroy(dronecu_env* env);
 int64_t dronecu_num_envs(const dronecu_env* env);
 int dronecu_obs_dim(const dronecu_env* env);
 int64_t dronecu_global_step(const dronecu_env* env); /* steps taken since create (Philox index) */
+int dronecu_set_global_step(dronecu_env* env, int64_t t); /* checkpoint restore of that index */
 double dronecu_motor_max(const dronecu_env* env);    /* 3*m*g/4, drone.py:263 */
 
 /* DroneGymEnv.reset (drone.py:270-271, :48-75) / VectorizedDroneGymEnv.reset
@@ -175,6 +176,89 @@ int dronecu_episode_stats(dronecu_env* env, dronecu_stats* h_out, int reset);
 
 /* Number of kernel launches this handle has issued (bench.py's gpu_launches). */
 uint64_t dronecu_launch_count(const dronecu_env* env);
+
+/* ------------------------------------------------------------------------------------------------
+ * PPO hot path (SB3 `PPO("MlpPolicy", env)` with every default: reference train.py:36-43).  The
+ * algorithm lives in stable-baselines3, which is NOT in the reference tree (environment.yaml:16);
+ * these entry points restate its published behaviour -- parity unpinned.
+ *
+ * Policy parameters are ONE flat float32 device vector of DRONECU_POLICY_PARAMS values:
+ *   pi.W1[64,15] pi.b1[64] pi.W2[64,64] pi.b2[64] pi.W3[4,64] pi.b3[4]
+ *   vf.W1[64,15] vf.b1[64] vf.W2[64,64] vf.b2[64] vf.W3[1,64] vf.b3[1]  log_std[4]
+ * (torch.nn.Linear [out,in] row-major blocks).
+ * ---------------------------------------------------------------------------------------------- */
+#define DRONECU_POLICY_PARAMS 10697
+#define DRONECU_GRAD_LEN (DRONECU_POLICY_PARAMS + 8) /* gradient sums + 8 statistics sums */
+
+/* Rollout-buffer outputs of dronecu_rollout_policy; any pointer may be NULL. */
+typedef struct dronecu_policy_out {
+  float* d_obs;        /* [K,n,15] observation each action was computed from (RolloutBuffer.observations) */
+  float* d_actions;    /* [K,n,4]  sampled action, unclipped (RolloutBuffer.actions)                      */
+  float* d_logp;       /* [K,n]    log-probability of the sampled action                                  */
+  float* d_value;      /* [K,n]    value estimate                                                         */
+  float* d_reward;     /* [K,n]                                                                           */
+  uint8_t* d_done;     /* [K,n]    episode ended at step k (== episode_start of step k+1)                 */
+  float* d_last_value; /* [n]      V(observation after the K-th step), the GAE bootstrap                  */
+  float* d_last_obs;   /* [n,15]   that observation                                                       */
+} dronecu_policy_out;
+
+/* SB3 collect_rollouts for K steps in ONE launch: per step a,v,logp = policy(obs); env.step(clip(a));
+ * auto-reset; episode statistics.  The env must use obs_dim 15 and DRONECU_AUTORESET.
+ * deterministic != 0: a = mean (PPO.predict(deterministic=True), reference test.py:14). */
+int dronecu_rollout_policy(dronecu_env* env, int K, const float* d_params, int deterministic,
+                           const dronecu_policy_out* out, void* stream);
+
+/* policy(obs): mean [B,4] and value [B] for arbitrary observation rows d_obs [B,15]
+ * (PPO.predict / policy.forward: reference train.py:48-50, test.py:14).  Outputs nullable. */
+int dronecu_policy_forward(int device, int64_t B, const float* d_params, const float* d_obs, float* d_mean,
+                           float* d_value, void* stream);
+
+/* RolloutBuffer.compute_returns_and_advantage: GAE(gamma, lambda) over [K,n] buffers. */
+int dronecu_gae(int device, int K, int64_t n, const float* d_reward, const float* d_value, const uint8_t* d_done,
+                const float* d_last_value, float gamma, float lam, float* d_advantage, float* d_returns, void* stream);
+
+typedef struct dronecu_ppo_config {
+  float learning_rate; /* 3e-4  */
+  float beta1, beta2;  /* 0.9, 0.999 */
+  float adam_eps;      /* 1e-5  */
+  float clip_range;    /* 0.2   */
+  float vf_coef;       /* 0.5   */
+  float ent_coef;      /* 0.0   */
+  float max_grad_norm; /* 0.5   */
+} dronecu_ppo_config;
+
+typedef struct dronecu_ppo dronecu_ppo; /* optimiser handle: Adam moments, step count, scratch */
+
+void dronecu_ppo_config_default(dronecu_ppo_config* cfg); /* the SB3 defaults listed above */
+int dronecu_ppo_create(const dronecu_ppo_config* cfg, int device, dronecu_ppo** out);
+int dronecu_ppo_destroy(dronecu_ppo* ppo);
+
+/* sum, sum of squares and count of the advantages of a minibatch, ACCUMULATED into d_out[3] (float64;
+ * zero it first).  Minibatch = rows d_index[0..m) of the flat buffers, or rows first..first+m when
+ * d_index is NULL.  (Data-parallel training all-reduces d_out before forming mean / std.) */
+int dronecu_ppo_adv_stats(dronecu_ppo* ppo, const float* d_adv, const int32_t* d_index, int64_t first, int64_t m,
+                          double* d_out, void* stream);
+
+/* Forward + backward of one minibatch: d_grad[DRONECU_GRAD_LEN] = SUM over the minibatch of the
+ * per-sample loss gradient (clipped surrogate + vf_coef * value MSE + ent_coef * entropy), followed by
+ * the sums of: policy loss, squared value error, approx_kl, clip fraction, sample count.  Advantages
+ * enter as (adv - adv_mean) * adv_inv_std; when d_adv_stats (the [sum, sumsq, count] written by
+ * dronecu_ppo_adv_stats) is not NULL, mean and 1/(unbiased std + 1e-8) are formed from it on the
+ * device instead -- no host round trip.  Deterministic for a fixed launch configuration. */
+int dronecu_ppo_grad(dronecu_ppo* ppo, const float* d_params, const float* d_obs, const float* d_actions,
+                     const float* d_old_logp, const float* d_adv, const float* d_returns, const int32_t* d_index,
+                     int64_t first, int64_t m, float adv_mean, float adv_inv_std, const double* d_adv_stats,
+                     float* d_grad, void* stream);
+
+/* clip_grad_norm_(max_grad_norm) + Adam.step() in place on d_params.  d_grad is the (all-reduced)
+ * output of dronecu_ppo_grad, inv_count = 1 / (global minibatch size).  d_info (nullable) receives
+ * [policy_loss, value_loss, approx_kl, clip_fraction, count, -, -, -, grad_norm]. */
+int dronecu_ppo_apply(dronecu_ppo* ppo, float* d_params, const float* d_grad, double inv_count, float* d_info,
+                      void* stream);
+int64_t dronecu_ppo_num_updates(const dronecu_ppo* ppo);
+/* Adam state access for checkpoints: copies [m | v] (2 * DRONECU_POLICY_PARAMS floats) device <-> device. */
+int dronecu_ppo_get_state(dronecu_ppo* ppo, float* d_moments, int64_t* h_step, void* stream);
+int dronecu_ppo_set_state(dronecu_ppo* ppo, const float* d_moments, int64_t step, void* stream);
 
 #ifdef __cplusplus
 }
