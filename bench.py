@@ -182,6 +182,8 @@ WORKLOAD_NAMES = {
     "c4": "configs[3] shard: step-only fused rollout, 8388608 envs/GPU (64M over 8), DroneGymEnv spec, Philox actions",
     "c2": "configs[1]: vectorized step-only, 4096 envs x 1000 steps, random actions streamed from HBM",
     "k1": "SB3 boundary: one env step per launch (dronecu_step), 8388608 envs/GPU, streamed actions",
+    "c3": "configs[2]: 1048576 envs fused K-step rollout with the PPO MLP policy/value forward in-kernel",
+    "c5": "configs[4]: full PPO loop (in-kernel-policy rollout + GAE + 10-epoch minibatch update, NCCL grad all-reduce)",
 }
 
 
@@ -328,6 +330,78 @@ def measure_e2e(drl, args, wl, n, rank, local, world, dist, barrier):
             "ms_per_call": 1e3 * dt / steps, "reward_checksum": checksum}
 
 
+def run_ppo(args):
+    """c3 (rollout with the in-kernel MLP) and c5 (full PPO iteration) -- env-steps/s."""
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device and no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import drone_rl_b200 as drl
+    from drone_rl_b200.ppo import PPO
+    wl = args.workload
+    n = args.ppo_envs
+    K = args.fuse
+    env = drl.DroneBatch(n, drl.EnvConfig.single(), device=local, seed=args.seed, env_offset=rank * n)
+    model = PPO(env, n_steps=K, batch_size=n * K // args.ppo_minibatches, n_epochs=args.ppo_epochs, seed=args.seed)
+
+    def one_step():
+        model.collect_rollouts()
+        if wl == "c5":
+            model.train()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        one_step()
+    barrier()
+    l0 = env.launch_count + model.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        ev0.record()
+        for _ in range(args.steps):
+            one_step()
+        ev1.record()
+        barrier()
+    launches = env.launch_count + model.launches - l0
+    t = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    value = n * K * args.steps * world / (total_ms * 1e-3)
+    flop_per_step = 20864.0 * (1 if wl == "c3" else 1 + 3 * args.ppo_epochs)
+    pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.isfile(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    peak = float(pk.get("bf16_tflops_sustained", 1400.0))
+    achieved = value / world * flop_per_step / 1e12
+    if rank == 0:
+        line = {"metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": WORKLOAD_NAMES[wl], "envs_per_gpu": n, "n_steps": K, "n_epochs": args.ppo_epochs,
+                           "minibatches_per_epoch": args.ppo_minibatches, "policy": "MlpPolicy 15-64-64-{4,1} tanh, random init",
+                           "l2": "rollout buffers %.1f GB per iteration, larger than L2" % (n * K * 93 / 1e9)},
+                "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                             "traffic": None, "note": "round-1 MLP kernels run on the fp32 CUDA cores (nominal 74.4 TFLOP/s FMA "
+                             "peak: frac_of_fp32 = %.3f); the denominator is the measured bf16 tensor peak" % (achieved / 74.4),
+                             "flop_per_env_step": flop_per_step},
+                "e2e": None, "gpu_launches": int(launches), "clocks": clocks.summary(),
+                "train": {k: v for k, v in model.logger_values.items() if k.startswith("train/")}}
+        print(json.dumps(line), flush=True)
+    model.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -340,10 +414,15 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the e2e leg (A/B kernel timing only)")
+    ap.add_argument("--ppo-envs", type=int, default=1_048_576)
+    ap.add_argument("--ppo-epochs", type=int, default=10)
+    ap.add_argument("--ppo-minibatches", type=int, default=4)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload in ("c3", "c5"):
+        run_ppo(args)
     else:
         run_gpu(args)
 

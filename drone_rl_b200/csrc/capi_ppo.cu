@@ -23,6 +23,7 @@ struct dronecu_ppo {
   int n_sm;
   float* partials;   // [n_sm, kGradLen]
   float* moments;    // [2, kParams]  Adam m | v
+  double* adv_partials; // [n_sm * 8, 2]
   int64_t step;
   uint64_t launches;
 };
@@ -107,6 +108,7 @@ extern "C" int dronecu_ppo_create(const dronecu_ppo_config* cfg, int device, dro
   CUDA_TRY(cudaDeviceGetAttribute(&p->n_sm, cudaDevAttrMultiProcessorCount, device));
   CUDA_TRY(cudaMalloc(&p->partials, sizeof(float) * (size_t)p->n_sm * kGradLen));
   CUDA_TRY(cudaMalloc(&p->moments, sizeof(float) * 2 * kParams));
+  CUDA_TRY(cudaMalloc(&p->adv_partials, sizeof(double) * 2 * (size_t)p->n_sm * 8));
   CUDA_TRY(cudaMemset(p->moments, 0, sizeof(float) * 2 * kParams));
   CUDA_TRY(cudaFuncSetAttribute(ppo_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UpdSmem)));
   *out = p;
@@ -117,7 +119,7 @@ extern "C" int dronecu_ppo_destroy(dronecu_ppo* p) {
   if (!p) return DRONECU_OK;
   DeviceGuard guard(p->device);
   cudaDeviceSynchronize();
-  cudaFree(p->partials); cudaFree(p->moments);
+  cudaFree(p->partials); cudaFree(p->moments); cudaFree(p->adv_partials);
   cudaGetLastError();
   delete p;
   return DRONECU_OK;
@@ -130,8 +132,10 @@ extern "C" int dronecu_ppo_adv_stats(dronecu_ppo* p, const float* d_adv, const i
   if (!p || !d_adv || !d_out || m <= 0) return fail(DRONECU_ERR_INVALID, "dronecu_ppo_adv_stats: bad argument");
   DeviceGuard guard(p->device);
   const unsigned grid = (unsigned)std::min<int64_t>((m + 255) / 256, (int64_t)p->n_sm * 8);
-  adv_stats_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_adv, d_index, first, m, d_out);
-  p->launches += 1;
+  adv_stats_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_adv, d_index, first, m, p->adv_partials);
+  CUDA_TRY(cudaGetLastError());
+  adv_stats_finish_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(p->adv_partials, (int)grid, m, d_out);
+  p->launches += 2;
   CUDA_TRY(cudaGetLastError());
   return DRONECU_OK;
 }

@@ -30,6 +30,7 @@ struct UpdSmem {
   float bufB[kUpdBlock][kRow];          // h2, later delta2
   float bufX[kUpdBlock][16];            // observation, x[15] = 1 (bias column)
   float g3[kUpdBlock][kAct];            // head gradient per sample
+  float wsum[kUpdBlock / 32][8];        // per-warp partial sums (log_std gradient, statistics)
 };
 
 struct UpdArgs {
@@ -308,20 +309,22 @@ __global__ void __launch_bounds__(kUpdBlock, 1) ppo_grad_kernel(const __grid_con
       st_cf = (fabsf(ratio - 1.0f) > A.clip) ? 1.0f : 0.f;
     }
     reinterpret_cast<float4*>(U.g3[tid])[0] = make_float4(g_pi[0], g_pi[1], g_pi[2], g_pi[3]);
-    // log_std gradient + statistics: warp sums, one shared-memory atomic per warp
+    // log_std gradient + statistics: warp sums -> smem -> fixed-order sum over the 4 warps (deterministic)
     {
       float v[7] = {g_ls[0], g_ls[1], g_ls[2], g_ls[3], st_pl, st_kl, st_cf};
 #pragma unroll
       for (int q = 0; q < 7; ++q) v[q] = warp_sum(v[q]);
       if (lane == 0) {
 #pragma unroll
-        for (int o = 0; o < kAct; ++o) atomicAdd(&U.G[O_LOGSTD + o], v[o]);
-        atomicAdd(&U.G[kParams + 0], v[4]);
-        atomicAdd(&U.G[kParams + 2], v[5]);
-        atomicAdd(&U.G[kParams + 3], v[6]);
+        for (int q = 0; q < 7; ++q) U.wsum[tid >> 5][q] = v[q];
       }
     }
-    __syncthreads();                                   // h2 (bufB), g3 complete for the whole tile
+    __syncthreads();                                   // h2 (bufB), g3, wsum complete for the whole tile
+    if (tid < 7) {
+      const float sum = ((U.wsum[0][tid] + U.wsum[1][tid]) + U.wsum[2][tid]) + U.wsum[3][tid];
+      const int dst = (tid < kAct) ? (O_LOGSTD + tid) : (tid == 4 ? kParams + 0 : (tid == 5 ? kParams + 2 : kParams + 3));
+      U.G[dst] += sum;
+    }
     wgrad_head<kAct>(U, O_PI_W3, O_PI_B3, rows);
     __syncthreads();                                   // dW3 has consumed h2
     float d1[kHid];
@@ -348,9 +351,10 @@ __global__ void __launch_bounds__(kUpdBlock, 1) ppo_grad_kernel(const __grid_con
     U.g3[tid][0] = g_v[0];
     {
       const float v0 = warp_sum(st_vl), v1 = warp_sum(live ? 1.0f : 0.f);
-      if (lane == 0) { atomicAdd(&U.G[kParams + 1], v0); atomicAdd(&U.G[kParams + 4], v1); }
+      if (lane == 0) { U.wsum[tid >> 5][0] = v0; U.wsum[tid >> 5][1] = v1; }
     }
     __syncthreads();
+    if (tid < 2) U.G[kParams + (tid == 0 ? 1 : 4)] += ((U.wsum[0][tid] + U.wsum[1][tid]) + U.wsum[2][tid]) + U.wsum[3][tid];
     wgrad_head<1>(U, O_VF_W3, O_VF_B3, rows);
     __syncthreads();
     tower_backward<1>(U, 1, g_v, U.bufA[tid], U.bufB[tid], d1);
@@ -378,9 +382,11 @@ __global__ void ppo_reduce_kernel(const float* __restrict__ partials, int n_part
   grad[idx] = sum;
 }
 
-// advantage statistics of a minibatch: out[0] += sum, out[1] += sum of squares, out[2] += count
+// advantage statistics of a minibatch, deterministic: per-CTA partial sums (float64) in a fixed
+// grid, then a one-thread fixed-order sum that ACCUMULATES [sum, sum of squares, count] into out[3]
 __global__ void adv_stats_kernel(const float* __restrict__ adv, const int32_t* __restrict__ index, int64_t first,
-                                 int64_t m, double* __restrict__ out) {
+                                 int64_t m, double* __restrict__ partial) {
+  __shared__ double sh[2][8];
   double s = 0.0, q = 0.0;
   for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < m; p += (int64_t)gridDim.x * blockDim.x) {
     const double a = (double)adv[index ? (int64_t)index[p] : first + p];
@@ -388,8 +394,24 @@ __global__ void adv_stats_kernel(const float* __restrict__ adv, const int32_t* _
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
-  if ((threadIdx.x & 31) == 0) { atomicAdd(&out[0], s); atomicAdd(&out[1], q); }
-  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&out[2], (double)m);
+  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = s; sh[1][threadIdx.x >> 5] = q; }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh[threadIdx.x][w];
+    partial[2 * blockIdx.x + threadIdx.x] = t;
+  }
+}
+
+__global__ void adv_stats_finish_kernel(const double* __restrict__ partial, int n_partials, int64_t m,
+                                        double* __restrict__ out) {
+  if (threadIdx.x < 2) {
+    double t = 0.0;
+    for (int p = 0; p < n_partials; ++p) t += partial[2 * p + threadIdx.x];
+    out[threadIdx.x] += t;
+  } else if (threadIdx.x == 2) {
+    out[2] += (double)m;
+  }
 }
 
 struct AdamArgs {
