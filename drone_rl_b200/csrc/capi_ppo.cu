@@ -131,7 +131,7 @@ extern "C" int dronecu_ppo_adv_stats(dronecu_ppo* p, const float* d_adv, const i
                                      int64_t m, double* d_out, void* stream) {
   if (!p || !d_adv || !d_out || m <= 0) return fail(DRONECU_ERR_INVALID, "dronecu_ppo_adv_stats: bad argument");
   DeviceGuard guard(p->device);
-  const unsigned grid = (unsigned)std::min<int64_t>((m + 255) / 256, (int64_t)p->n_sm * 8);
+  const unsigned grid = (unsigned)std::min<int64_t>((m + 255) / 256, (int64_t)p->n_sm * 4);
   adv_stats_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_adv, d_index, first, m, p->adv_partials);
   CUDA_TRY(cudaGetLastError());
   adv_stats_finish_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(p->adv_partials, (int)grid, m, d_out);

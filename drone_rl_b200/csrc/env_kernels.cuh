@@ -58,15 +58,15 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 // sequence costs more issue slots per warp-step than 4 LDS.128 + 4 STG.128.
 template <int OBS_DIM>
 __device__ __forceinline__ void emit_obs_rows(float* tile, float* gdst, const EnvState& s, int lane,
-                                              int valid, bool active) {
+                                              int valid, bool active, bool fast) {
+  float* const row = tile + lane * OBS_DIM;
   constexpr int kQuads = 32 * OBS_DIM / 4;
-  const bool aligned = (valid == 32) && ((reinterpret_cast<uintptr_t>(gdst) & 15) == 0);
 #if DRONECU_EMIT_BULK
   constexpr uint32_t kBytes = 32 * OBS_DIM * sizeof(float);
   if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   __syncwarp();
-  if (active) write_obs<OBS_DIM>(tile + lane * OBS_DIM, s);
-  if (aligned) {
+  if (active) write_obs<OBS_DIM>(row, s);
+  if (fast) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
     if (lane == 0) {
@@ -78,8 +78,8 @@ __device__ __forceinline__ void emit_obs_rows(float* tile, float* gdst, const En
   }
 #else
   __syncwarp();     // the previous step's read-back of this tile is complete
-  if (active) write_obs<OBS_DIM>(tile + lane * OBS_DIM, s);
-  if (aligned) {
+  if (active) write_obs<OBS_DIM>(row, s);
+  if (fast) {       // full warp, 16-byte aligned destination rows: 128-bit read-back + store
     __syncwarp();
     const float4* t4 = reinterpret_cast<const float4*>(tile);
     float4* g4 = reinterpret_cast<float4*>(gdst);
@@ -91,6 +91,14 @@ __device__ __forceinline__ void emit_obs_rows(float* tile, float* gdst, const En
   __syncwarp();
   for (int j = lane; j < valid * OBS_DIM; j += 32) gdst[j] = tile[j];
   __syncwarp();
+}
+
+// can every [n,D] row block of this warp take the 128-bit path?  (full warp; base 16-byte aligned;
+// consecutive [n,D] slabs keep the alignment when n*D is a multiple of 4 floats)
+template <int OBS_DIM>
+__device__ __forceinline__ bool emit_fast_ok(const float* base, int64_t warp_base, int64_t n, int valid) {
+  return (valid == 32) && ((reinterpret_cast<uintptr_t>(base + warp_base * OBS_DIM) & 15) == 0) &&
+         (((n * OBS_DIM) & 3) == 0);
 }
 
 // RECORD = true: the "rollout record" output set -- next_obs, reward, done (and the applied action
@@ -118,10 +126,12 @@ __global__ void __launch_bounds__(kBlock, DRONECU_MIN_BLOCKS) rollout_kernel(con
   if (active) s = load_state(A.state, i);
 
   if (A.obs0 != nullptr && valid > 0)
-    emit_obs_rows<OBS_DIM>(tile, A.obs0 + warp_base * OBS_DIM, s, lane, valid, active);
+    emit_obs_rows<OBS_DIM>(tile, A.obs0 + warp_base * OBS_DIM, s, lane, valid, active,
+                           emit_fast_ok<OBS_DIM>(A.obs0, warp_base, A.n, valid));
 
   uint32_t n_done = 0, n_term = 0, len_sum = 0;
   float ret_sum = 0.f;
+  const bool fast_obs = emit_fast_ok<OBS_DIM>(A.next_obs, warp_base, A.n, valid);
 
   // running output pointers: one 64-bit add per output per step instead of k*n + i each time
   const int64_t n = A.n;
@@ -178,7 +188,7 @@ __global__ void __launch_bounds__(kBlock, DRONECU_MIN_BLOCKS) rollout_kernel(con
         }
       }
     }
-    if (w_obs && valid > 0) emit_obs_rows<OBS_DIM>(tile, p_obs, s, lane, valid, active);
+    if (w_obs && valid > 0) emit_obs_rows<OBS_DIM>(tile, p_obs, s, lane, valid, active, fast_obs);
     p_act_out += n; p_rew += n; p_done += n; p_trunc += n; p_obs += n * OBS_DIM; row += n;
   }
 
@@ -235,7 +245,8 @@ __global__ void __launch_bounds__(kBlock) reset_kernel(StatePlanes sp, const __g
     }
   }
   if (obs != nullptr && valid > 0)
-    emit_obs_rows<OBS_DIM>(tiles[warp], obs + warp_base * OBS_DIM, s, lane, valid, active);
+    emit_obs_rows<OBS_DIM>(tiles[warp], obs + warp_base * OBS_DIM, s, lane, valid, active,
+                           emit_fast_ok<OBS_DIM>(obs, warp_base, n, valid));
 #if DRONECU_EMIT_BULK
   if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 #endif

@@ -169,10 +169,12 @@ __global__ void __launch_bounds__(kPolBlock) policy_rollout_kernel(const __grid_
   uint8_t* p_done = A.done + i;
   float* p_obs = A.obs + warp_base * kObs;
 
+  const bool fast_obs = emit_fast_ok<kObs>(A.obs, warp_base, n, valid);
+
   for (int k = 0; k < A.K; ++k) {
     float x[kObs];
     write_obs<kObs>(x, s);
-    if (A.obs != nullptr && valid > 0) emit_obs_rows<kObs>(tile, p_obs, s, lane, valid, active);
+    if (A.obs != nullptr && valid > 0) emit_obs_rows<kObs>(tile, p_obs, s, lane, valid, active, fast_obs);
 
     float mean[kAct], val[1];
     tower_forward<kAct>(S, 0, x, mean);
@@ -221,7 +223,8 @@ __global__ void __launch_bounds__(kPolBlock) policy_rollout_kernel(const __grid_
       if (active) A.last_value[i] = val[0];
     }
     if (A.last_obs != nullptr && valid > 0)
-      emit_obs_rows<kObs>(tile, A.last_obs + warp_base * kObs, s, lane, valid, active);
+      emit_obs_rows<kObs>(tile, A.last_obs + warp_base * kObs, s, lane, valid, active,
+                          emit_fast_ok<kObs>(A.last_obs, warp_base, n, valid));
   }
   if (active) store_state(A.state, i, s);
 

@@ -405,13 +405,12 @@ __global__ void adv_stats_kernel(const float* __restrict__ adv, const int32_t* _
 
 __global__ void adv_stats_finish_kernel(const double* __restrict__ partial, int n_partials, int64_t m,
                                         double* __restrict__ out) {
-  if (threadIdx.x < 2) {
-    double t = 0.0;
-    for (int p = 0; p < n_partials; ++p) t += partial[2 * p + threadIdx.x];
-    out[threadIdx.x] += t;
-  } else if (threadIdx.x == 2) {
-    out[2] += (double)m;
-  }
+  // one warp; lane l sums partials l, l+32, ... in order, then a fixed shuffle tree: deterministic
+  double s = 0.0, q = 0.0;
+  for (int p = threadIdx.x; p < n_partials; p += 32) { s += partial[2 * p]; q += partial[2 * p + 1]; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+  if (threadIdx.x == 0) { out[0] += s; out[1] += q; out[2] += (double)m; }
 }
 
 struct AdamArgs {
