@@ -349,7 +349,8 @@ def run_ppo(args):
     n = args.ppo_envs
     K = args.fuse
     env = drl.DroneBatch(n, drl.EnvConfig.single(), device=local, seed=args.seed, env_offset=rank * n)
-    model = PPO(env, n_steps=K, batch_size=n * K // args.ppo_minibatches, n_epochs=args.ppo_epochs, seed=args.seed)
+    model = PPO(env, n_steps=K, batch_size=n * K // args.ppo_minibatches, n_epochs=args.ppo_epochs, seed=args.seed,
+                rollout_precision=args.precision)
 
     def one_step():
         model.collect_rollouts()
@@ -387,7 +388,7 @@ def run_ppo(args):
                 "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": WORKLOAD_NAMES[wl], "envs_per_gpu": n, "n_steps": K, "n_epochs": args.ppo_epochs,
-                           "minibatches_per_epoch": args.ppo_minibatches, "policy": "MlpPolicy 15-64-64-{4,1} tanh, random init",
+                           "minibatches_per_epoch": args.ppo_minibatches, "policy": "MlpPolicy 15-64-64-{4,1} tanh, random init", "rollout_precision": args.precision,
                            "l2": "rollout buffers %.1f GB per iteration, larger than L2" % (n * K * 93 / 1e9)},
                 "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                              "traffic": None, "note": "round-1 MLP kernels run on the fp32 CUDA cores (nominal 74.4 TFLOP/s FMA "
@@ -417,6 +418,7 @@ def main():
     ap.add_argument("--ppo-envs", type=int, default=1_048_576)
     ap.add_argument("--ppo-epochs", type=int, default=10)
     ap.add_argument("--ppo-minibatches", type=int, default=4)
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32"], help="policy MLP in the rollout: CUDA cores or tcgen05")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -11,6 +11,7 @@
 #include "capi_common.h"
 #include "env_handle.h"
 #include "ppo_update.cuh"
+#include "ppo_rollout_tc.cuh"
 
 using namespace dronecu;
 
@@ -28,8 +29,8 @@ struct dronecu_ppo {
   uint64_t launches;
 };
 
-extern "C" int dronecu_rollout_policy(dronecu_env* e, int K, const float* d_params, int deterministic,
-                                      const dronecu_policy_out* out, void* stream) {
+static int rollout_policy_impl(dronecu_env* e, int K, const float* d_params, int deterministic,
+                               const dronecu_policy_out* out, void* stream, bool tensor_cores) {
   if (!e || !d_params) return fail(DRONECU_ERR_INVALID, "dronecu_rollout_policy: null argument");
   if (K <= 0) return fail(DRONECU_ERR_INVALID, "K must be positive");
   if (e->cfg.obs_dim != 15 || !(e->cfg.flags & DRONECU_AUTORESET))
@@ -48,7 +49,16 @@ extern "C" int dronecu_rollout_policy(dronecu_env* e, int K, const float* d_para
   }
   const unsigned grid = (unsigned)((e->n + kPolBlock - 1) / kPolBlock);
   cudaStream_t st = (cudaStream_t)stream;
-  if (e->cfg.flags & DRONECU_RANDOMIZED) {
+  if (tensor_cores) {
+    static_assert(tc::kTile == kPolBlock, "tile size");
+    if (e->cfg.flags & DRONECU_RANDOMIZED) {
+      CUDA_TRY(cudaFuncSetAttribute(policy_rollout_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
+      policy_rollout_tc_kernel<true><<<grid, tc::kTile, kTcSmem, st>>>(a);
+    } else {
+      CUDA_TRY(cudaFuncSetAttribute(policy_rollout_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
+      policy_rollout_tc_kernel<false><<<grid, tc::kTile, kTcSmem, st>>>(a);
+    }
+  } else if (e->cfg.flags & DRONECU_RANDOMIZED) {
     CUDA_TRY(cudaFuncSetAttribute(policy_rollout_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPolicySmem));
     policy_rollout_kernel<true><<<grid, kPolBlock, kPolicySmem, st>>>(a);
   } else {
@@ -59,6 +69,29 @@ extern "C" int dronecu_rollout_policy(dronecu_env* e, int K, const float* d_para
   CUDA_TRY(cudaGetLastError());
   e->t += (uint64_t)K;
   e->env_steps += (uint64_t)K * (uint64_t)e->n;
+  return DRONECU_OK;
+}
+
+extern "C" int dronecu_rollout_policy(dronecu_env* e, int K, const float* d_params, int deterministic,
+                                      const dronecu_policy_out* out, void* stream) {
+  return rollout_policy_impl(e, K, d_params, deterministic, out, stream, false);
+}
+
+extern "C" int dronecu_rollout_policy_tc(dronecu_env* e, int K, const float* d_params, int deterministic,
+                                         const dronecu_policy_out* out, void* stream) {
+  return rollout_policy_impl(e, K, d_params, deterministic, out, stream, true);
+}
+
+extern "C" int dronecu_policy_forward_tc(int device, int64_t B, const float* d_params, const float* d_obs, float* d_mean,
+                                         float* d_value, float* d_dbg1, float* d_dbg2, void* stream) {
+  if (B <= 0 || !d_params || !d_obs) return fail(DRONECU_ERR_INVALID, "dronecu_policy_forward_tc: bad argument");
+  if (d_mean && (reinterpret_cast<uintptr_t>(d_mean) & 15)) return fail(DRONECU_ERR_INVALID, "d_mean must be 16-byte aligned");
+  DeviceGuard guard(device);
+  CUDA_TRY(cudaFuncSetAttribute(policy_forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
+  const unsigned grid = (unsigned)std::min<int64_t>((B + tc::kTile - 1) / tc::kTile, 148 * 2);
+  policy_forward_tc_kernel<<<grid, tc::kTile, kTcSmem, (cudaStream_t)stream>>>(d_params, d_obs, B, reinterpret_cast<float4*>(d_mean),
+                                                                              d_value, d_dbg1, d_dbg2);
+  CUDA_TRY(cudaGetLastError());
   return DRONECU_OK;
 }
 

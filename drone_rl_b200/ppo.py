@@ -97,7 +97,8 @@ class PPO:
     def __init__(self, env=1, n_steps: int = 2048, batch_size: int = 64, n_epochs: int = 10, gamma: float = 0.99,
                  gae_lambda: float = 0.95, clip_range: float = 0.2, ent_coef: float = 0.0, vf_coef: float = 0.5,
                  max_grad_norm: float = 0.5, learning_rate: float = 3e-4, normalize_advantage: bool = True,
-                 seed: int = 0, device: int = 0, verbose: int = 0, policy_seed: Optional[int] = None):
+                 seed: int = 0, device: int = 0, verbose: int = 0, policy_seed: Optional[int] = None,
+                 rollout_precision: str = "fp32"):
         self.lib = _lib.load()
         self.rank, self.world = 0, 1
         if torch.distributed.is_available() and torch.distributed.is_initialized():
@@ -111,6 +112,9 @@ class PPO:
         self.n_envs, self.n_steps, self.batch_size, self.n_epochs = self.batch.n, n_steps, batch_size, n_epochs
         self.gamma, self.gae_lambda, self.normalize_advantage = gamma, gae_lambda, normalize_advantage
         self.verbose, self.seed = verbose, seed
+        if rollout_precision not in ("fp32", "tf32"):
+            raise ValueError("rollout_precision must be 'fp32' (CUDA cores, parity path) or 'tf32' (tcgen05 tensor cores)")
+        self.rollout_precision = rollout_precision
         cfg = PPOConfig()
         self.lib.dronecu_ppo_config_default(C.byref(cfg))
         cfg.learning_rate, cfg.clip_range, cfg.ent_coef = learning_rate, clip_range, ent_coef
@@ -149,8 +153,8 @@ class PPO:
         out = PolicyOut(b.obs.data_ptr(), b.actions.data_ptr(), b.logp.data_ptr(), b.value.data_ptr(),
                         b.reward.data_ptr(), b.done.data_ptr(), b.last_value.data_ptr(), None)
         st = _stream_ptr(self.device)
-        _lib.check(self.lib.dronecu_rollout_policy(self.batch._h, K, _ptr(self.params), int(deterministic),
-                                                   C.byref(out), st), "dronecu_rollout_policy")
+        fn = self.lib.dronecu_rollout_policy_tc if self.rollout_precision == "tf32" else self.lib.dronecu_rollout_policy
+        _lib.check(fn(self.batch._h, K, _ptr(self.params), int(deterministic), C.byref(out), st), "dronecu_rollout_policy")
         _lib.check(self.lib.dronecu_gae(self.device.index, K, n, _ptr(b.reward), _ptr(b.value), _ptr(b.done),
                                         _ptr(b.last_value), self.gamma, self.gae_lambda, _ptr(b.adv), _ptr(b.ret), st),
                    "dronecu_gae")
@@ -218,12 +222,20 @@ class PPO:
         return self
 
     # -- inference ----------------------------------------------------------------------------------
-    def policy_forward(self, obs: torch.Tensor):
-        """(mean [B,4], value [B]) for device observations [B,15]."""
+    def policy_forward(self, obs: torch.Tensor, precision: str = "fp32", debug: bool = False):
+        """(mean [B,4], value [B]) for device observations [B,15].  precision "tf32" runs the tcgen05
+        kernel; with debug=True it also returns the layer-1 / layer-2 pre-activations [B,128] each."""
         obs = obs.to(self.device, torch.float32).contiguous()
         B = obs.shape[0]
         mean = torch.empty(B, 4, dtype=torch.float32, device=self.device)
         value = torch.empty(B, dtype=torch.float32, device=self.device)
+        if precision == "tf32":
+            d1 = torch.zeros(B, 128, dtype=torch.float32, device=self.device) if debug else None
+            d2 = torch.zeros(B, 128, dtype=torch.float32, device=self.device) if debug else None
+            _lib.check(self.lib.dronecu_policy_forward_tc(self.device.index, B, _ptr(self.params), _ptr(obs), _ptr(mean),
+                                                          _ptr(value), _ptr(d1), _ptr(d2), _stream_ptr(self.device)),
+                       "dronecu_policy_forward_tc")
+            return (mean, value, d1, d2) if debug else (mean, value)
         _lib.check(self.lib.dronecu_policy_forward(self.device.index, B, _ptr(self.params), _ptr(obs), _ptr(mean),
                                                    _ptr(value), _stream_ptr(self.device)), "dronecu_policy_forward")
         return mean, value

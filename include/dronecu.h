@@ -208,6 +208,14 @@ typedef struct dronecu_policy_out {
 int dronecu_rollout_policy(dronecu_env* env, int K, const float* d_params, int deterministic,
                            const dronecu_policy_out* out, void* stream);
 
+/* Tensor-core variant (tcgen05 + TMEM, tf32 products, fp32 accumulation, tanh.approx): same contract,
+ * outputs within ~2e-3 of dronecu_rollout_policy's; the fp32 entry point stays the parity path. */
+int dronecu_rollout_policy_tc(dronecu_env* env, int K, const float* d_params, int deterministic,
+                              const dronecu_policy_out* out, void* stream);
+/* d_dbg1 / d_dbg2 (nullable, [B,128] each): layer-1 / layer-2 pre-activations (pi 0..63 | vf 64..127). */
+int dronecu_policy_forward_tc(int device, int64_t B, const float* d_params, const float* d_obs, float* d_mean,
+                              float* d_value, float* d_dbg1, float* d_dbg2, void* stream);
+
 /* policy(obs): mean [B,4] and value [B] for arbitrary observation rows d_obs [B,15]
  * (PPO.predict / policy.forward: reference train.py:48-50, test.py:14).  Outputs nullable. */
 int dronecu_policy_forward(int device, int64_t B, const float* d_params, const float* d_obs, float* d_mean,
