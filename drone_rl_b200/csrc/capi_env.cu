@@ -3,6 +3,7 @@
 // fallback: every entry point needs a CUDA device and reports a CUDA error otherwise.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -173,6 +174,7 @@ extern "C" int dronecu_destroy(dronecu_env* e) {
   cudaFree(e->d_done); cudaFree(e->d_trunc); cudaFree(e->d_mask); cudaFree(e->d_ep_r); cudaFree(e->d_ep_l);
   cudaFree(e->d_view_f); cudaFree(e->d_view_i);
   if (e->io_stream) cudaStreamDestroy(e->io_stream);
+  if (e->io_stream2) cudaStreamDestroy(e->io_stream2);
   cudaGetLastError();
   delete e;
   return DRONECU_OK;
@@ -244,6 +246,7 @@ static int ensure_io(dronecu_env* e) {
   if (e->io_stream) return DRONECU_OK;
   const size_t n = (size_t)e->n, D = (size_t)e->cfg.obs_dim;
   CUDA_TRY(cudaStreamCreateWithFlags(&e->io_stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamCreateWithFlags(&e->io_stream2, cudaStreamNonBlocking));
   CUDA_TRY(cudaMalloc(&e->d_act, n * 4 * sizeof(float)));
   CUDA_TRY(cudaMalloc(&e->d_obs, n * D * sizeof(float)));
   CUDA_TRY(cudaMalloc(&e->d_term, n * D * sizeof(float)));
@@ -258,14 +261,41 @@ static int ensure_io(dronecu_env* e) {
   return DRONECU_OK;
 }
 
+// One env step over the sub-range [first, first + count) of the handle's envs (K = 1 only: every
+// [n, .] output row block is addressed by env index, so a range is a pointer offset).  Does not advance
+// the handle's step counters -- the caller does that once per full step.
+static int launch_step_range(dronecu_env* e, const float* d_actions, const dronecu_step_out& d, int64_t first,
+                             int64_t count, cudaStream_t st) {
+  const int64_t D = e->cfg.obs_dim;
+  RolloutArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.state = e->sp;
+  for (int k = 0; k < 5; ++k) a.state.q[k] += first;
+  a.P = e->P; a.P.env_offset += (uint64_t)first;
+  a.n = count; a.K = 1; a.t0 = e->t; a.stats = e->stats;
+  a.actions = reinterpret_cast<const float4*>(d_actions) + first;
+  a.next_obs = d.d_obs ? d.d_obs + first * D : nullptr;
+  a.reward = d.d_reward ? d.d_reward + first : nullptr;
+  a.done = d.d_done ? d.d_done + first : nullptr;
+  a.truncated = d.d_truncated ? d.d_truncated + first : nullptr;
+  a.terminal_obs = d.d_terminal_obs ? d.d_terminal_obs + first * D : nullptr;
+  a.episode_r = d.d_episode_r ? d.d_episode_r + first : nullptr;
+  a.episode_l = d.d_episode_l ? d.d_episode_l + first : nullptr;
+  const uint64_t t_keep = e->t, s_keep = e->env_steps;
+  dronecu_env tmp_view = *e;          // launch_rollout reads n / cfg from the handle: use a shallow view
+  tmp_view.n = count;
+  int rc = launch_rollout(&tmp_view, a, DRONECU_ACTIONS_STREAMED, st);
+  e->launches += 1;
+  e->t = t_keep; e->env_steps = s_keep;
+  return rc;
+}
+
 extern "C" int dronecu_step_host(dronecu_env* e, const float* h_actions, const dronecu_step_out* h) {
   if (!e || !h_actions || !h) return fail(DRONECU_ERR_INVALID, "dronecu_step_host: null argument");
   DeviceGuard guard(e->device);
   int rc = ensure_io(e);
   if (rc) return rc;
-  const size_t n = (size_t)e->n, D = (size_t)e->cfg.obs_dim;
-  cudaStream_t st = e->io_stream;
-  CUDA_TRY(cudaMemcpyAsync(e->d_act, h_actions, n * 4 * sizeof(float), cudaMemcpyHostToDevice, st));
+  const int64_t n = e->n, D = e->cfg.obs_dim;
   dronecu_step_out d;
   d.d_obs = h->d_obs ? e->d_obs : nullptr;
   d.d_reward = h->d_reward ? e->d_rew : nullptr;
@@ -274,14 +304,29 @@ extern "C" int dronecu_step_host(dronecu_env* e, const float* h_actions, const d
   d.d_terminal_obs = h->d_terminal_obs ? e->d_term : nullptr;
   d.d_episode_r = h->d_episode_r ? e->d_ep_r : nullptr;
   d.d_episode_l = h->d_episode_l ? e->d_ep_l : nullptr;
-  rc = dronecu_step(e, e->d_act, &d, st);
-  if (rc) return rc;
-#define COPY_OUT(field, bytes) if (h->field) CUDA_TRY(cudaMemcpyAsync(h->field, d.field, bytes, cudaMemcpyDeviceToHost, st));
-  COPY_OUT(d_obs, n * D * sizeof(float)) COPY_OUT(d_reward, n * sizeof(float)) COPY_OUT(d_done, n)
-  COPY_OUT(d_truncated, n) COPY_OUT(d_terminal_obs, n * D * sizeof(float))
-  COPY_OUT(d_episode_r, n * sizeof(float)) COPY_OUT(d_episode_l, n * sizeof(int32_t))
+  // Large batches are cut into chunks that alternate between two streams, so the H2D copy of chunk
+  // c+1 and the kernel of chunk c run under the D2H copy of chunk c-1 (PCIe is full duplex; the D2H of
+  // the observations, 60 of the 82 bytes per env-step, is the long pole).
+  const int64_t kChunk = 1 << 20;
+  const int n_chunks = n >= 2 * kChunk ? (int)((n + kChunk - 1) / kChunk) : 1;
+  cudaStream_t streams[2] = {e->io_stream, e->io_stream2};
+  for (int c = 0; c < n_chunks; ++c) {
+    const int64_t first = (int64_t)c * kChunk, count = std::min<int64_t>(kChunk, n - first);
+    const size_t cnt = (size_t)count;
+    cudaStream_t st = streams[c & 1];
+    CUDA_TRY(cudaMemcpyAsync(e->d_act + first * 4, h_actions + first * 4, cnt * 4 * sizeof(float), cudaMemcpyHostToDevice, st));
+    rc = launch_step_range(e, e->d_act, d, first, count, st);
+    if (rc) return rc;
+#define COPY_OUT(field, stride, esize) if (h->field) CUDA_TRY(cudaMemcpyAsync(h->field + first * (stride), d.field + first * (stride), cnt * (stride) * (esize), cudaMemcpyDeviceToHost, st));
+    COPY_OUT(d_obs, D, sizeof(float)) COPY_OUT(d_reward, 1, sizeof(float)) COPY_OUT(d_done, 1, 1)
+    COPY_OUT(d_truncated, 1, 1) COPY_OUT(d_terminal_obs, D, sizeof(float))
+    COPY_OUT(d_episode_r, 1, sizeof(float)) COPY_OUT(d_episode_l, 1, sizeof(int32_t))
 #undef COPY_OUT
-  CUDA_TRY(cudaStreamSynchronize(st));
+  }
+  e->t += 1;
+  e->env_steps += (uint64_t)n;
+  CUDA_TRY(cudaStreamSynchronize(e->io_stream));
+  if (n_chunks > 1) CUDA_TRY(cudaStreamSynchronize(e->io_stream2));
   return DRONECU_OK;
 }
 

@@ -19,6 +19,7 @@ struct dronecu_env {
   uint64_t env_steps;
   // device + stream used by the *_host entry points (lazily created)
   cudaStream_t io_stream;
+  cudaStream_t io_stream2;   // second stream: chunked step_host overlaps H2D, kernel and D2H
   float *d_act, *d_obs, *d_rew, *d_term;
   uint8_t *d_done, *d_trunc, *d_mask;
   float* d_ep_r;

@@ -420,3 +420,27 @@ def test_full_size_rollout_properties(drl):
     assert torch.equal(nxt2, nxt[:, 3 * q:])
     print("full-size:", rep)
     b.close(); b2.close()
+
+
+def test_chunked_host_step_equals_device_step(drl):
+    """dronecu_step_host cuts large batches into 1M-env chunks on two streams (H2D / kernel / D2H
+    overlap); the result must be bit-identical to the single device-pointer launch, ragged tail included."""
+    n = (1 << 21) + 1000
+    rng = np.random.default_rng(3)
+    acts = rng.uniform(0, 7.3575, (n, 4)).astype(np.float32)
+    venv = drl.DroneVecEnv(n, seed=9, info_mode="arrays", copy=False)
+    ref = drl.DroneBatch(n, drl.EnvConfig.single(), seed=9)
+    o_h = venv.reset().copy()
+    o_d = ref.reset()
+    assert np.array_equal(o_h, o_d.cpu().numpy())
+    a_dev = torch.from_numpy(acts).cuda()
+    for _ in range(3):
+        obs, rew, done, info = venv.step(acts)
+        out = ref.step(a_dev, want_truncated=True)
+        assert np.array_equal(obs, out["obs"].cpu().numpy())
+        assert np.array_equal(rew, out["reward"].cpu().numpy())
+        assert np.array_equal(done, out["done"].cpu().numpy().astype(bool))
+        assert np.array_equal(info["truncated"], out["truncated"].cpu().numpy().astype(bool))
+    assert venv.batch.global_step == ref.global_step == 3
+    assert venv.episode_stats()["env_steps"] == 3 * n
+    venv.close(); ref.close()
