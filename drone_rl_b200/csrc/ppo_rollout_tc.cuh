@@ -6,13 +6,10 @@
 
 namespace dronecu {
 
-constexpr size_t kTcSmem = sizeof(tc::Smem) + (tc::kTile / 32) * 32 * kObs * sizeof(float) + 128;
+constexpr size_t kTcSmem = sizeof(tc::Smem) + (tc::kTile / 32) * 32 * kObs * sizeof(float);
 
-__device__ __forceinline__ tc::Smem& tc_smem(unsigned char* raw) {
-  uintptr_t p = reinterpret_cast<uintptr_t>(raw);
-  p = (p + 127) & ~uintptr_t(127);
-  return *reinterpret_cast<tc::Smem*>(p);
-}
+// no integer round trip: the compiler must keep seeing a shared-memory pointer (LDS, not generic LD)
+__device__ __forceinline__ tc::Smem& tc_smem(unsigned char* raw) { return *reinterpret_cast<tc::Smem*>(raw); }
 
 __global__ void __launch_bounds__(tc::kTile) policy_forward_tc_kernel(const float* __restrict__ theta,
                                                                        const float* __restrict__ obs, int64_t B,
@@ -116,10 +113,10 @@ __global__ void __launch_bounds__(tc::kTile) policy_rollout_tc_kernel(const __gr
   }
 
   {
-    float x[kObs], mean[kAct], val;
+    float x[kObs], val;
     write_obs<kObs>(x, s);
     if (A.last_value != nullptr) {       // uniform across the CTA: every thread takes part in the forward
-      tc::forward(S, x, phase, mean, val);
+      val = tc::forward_value(S, x, phase);
       if (active) A.last_value[i] = val;
     }
     if (A.last_obs != nullptr && valid > 0)

@@ -1,18 +1,19 @@
 // Policy / value MLP forward on the 5th-generation tensor cores (tcgen05 + TMEM), hand-written PTX.
 //
 // Tile = 128 envs = the 128 threads of a CTA = the 128 lanes of TMEM: thread i owns env i, TMEM lane i
-// and row i of every accumulator.  Per forward:
+// and row i of every accumulator.  Per forward, for each tower t in (pi, vf):
 //   X  [128 x 16]  (obs | 1.0)     -> tcgen05.st into TMEM columns (A operand, K-major, tf32)
-//   D1 [128 x 128] = X . W1cat^T   one MMA chain, N = 128 (64 pi units | 64 vf units), bias folded in
-//                                   through the ones column                        (2 MMAs, K = 8 each)
+//   D1 [128 x 64]  = X . W1t^T      bias folded in through the ones column       (2 MMAs, K = 8 each)
 //   H1 = tanh(D1)                   tcgen05.ld -> MUFU tanh -> tcgen05.st back IN PLACE (A operand of L2)
-//   D2t[128 x 64]  = H1t . W2t^T    per tower t, A from TMEM, B from shared memory  (2 x 8 MMAs)
-//   H2 = tanh(D2 + b2), heads       tcgen05.ld -> registers; the 4+1 head outputs are 320 FMAs per env
-//                                   on the CUDA cores (N = 5 is below the MMA's minimum N of 16)
+//   D2 [128 x 64]  = H1 . W2t^T     A from TMEM, B from shared memory              (8 MMAs, K = 8 each)
+//   H2 = tanh(D2 + b2), head        tcgen05.ld -> registers; the 4 (or 1) head outputs are 256 (64) FMAs
+//                                   per env on the CUDA cores (N = 4 is below the MMA's minimum N of 16)
 // Weights (B operands) sit in shared memory in the canonical no-swizzle K-major UMMA layout
 // (8-row x 16-byte core matrices; LBO = 128 B between K chunks, SBO = K*32 B between 8-row groups),
-// rounded once to tf32.  TMEM budget: 256 columns per CTA (D1/H1 128 | D2 128, X aliases D2) so two
-// CTAs share an SM's 512 columns and one CTA's MMA / TMEM traffic overlaps the other's MUFU work.
+// rounded once to tf32.  TMEM budget: 128 columns per CTA (D1/H1 64 | D2 64, X aliases D2), so FOUR
+// CTAs share an SM's 512 columns: the MUFU-bound tanh work of one CTA runs under the MMA / mbarrier
+// latency of the others (round-1 ncu: the 256-column, both-towers-at-once variant left the SM at 40 %
+// issue utilisation with 8 resident warps).
 // Precision: tf32 products (10-bit mantissa), fp32 accumulation, tanh.approx.f32 (2^-11): outputs agree
 // with the fp32 CUDA-core path to ~2e-3; that path stays the parity reference (tests/test_gpu_ppo.py).
 #pragma once
@@ -22,14 +23,14 @@ namespace dronecu {
 namespace tc {
 
 constexpr int kTile = 128;          // envs per CTA == threads per CTA == TMEM lanes
-constexpr int kTmemCols = 256;
-constexpr int kColD1 = 0;           // D1 / H1 : columns [0,128)
-constexpr int kColD2 = 128;         // D2      : columns [128,256) (pi 128..191, vf 192..255)
-constexpr int kColX = 128;          // X       : columns [128,144), dead before D2 is written
-constexpr int kK1 = 16, kN1 = 128, kK2 = 64, kN2 = 64;
+constexpr int kTmemCols = 128;
+constexpr int kColD1 = 0;           // D1 / H1 : columns [0,64)
+constexpr int kColD2 = 64;          // D2      : columns [64,128)
+constexpr int kColX = 64;           // X       : columns [64,80), dead before D2 is written
+constexpr int kK1 = 16, kN1 = 64, kK2 = 64, kN2 = 64;
 
 struct alignas(128) Smem {
-  float W1[kN1 * kK1];              // canonical UMMA layout, [n][k] = W1cat[n][k], k = 15 holds the bias
+  float W1[2][kN1 * kK1];           // canonical UMMA layout per tower, k = 15 holds the bias
   float W2[2][kN2 * kK2];           // canonical UMMA layout per tower
   float b2[2][kHid];
   float W3piT[kHid][kAct];
@@ -48,6 +49,10 @@ __device__ __forceinline__ float to_tf32(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
 }
+
+// round-to-nearest tf32 for values that are never inf: the tensor core ignores the low 13 mantissa
+// bits, so adding half an ulp of tf32 is all it takes (cvt.rna.tf32 compiles to 3 instructions)
+__device__ __forceinline__ float to_tf32_fast(float x) { return __uint_as_float(__float_as_uint(x) + 0x1000u); }
 
 __device__ __forceinline__ float tanh_mufu(float x) {
   float y;
@@ -133,12 +138,12 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) 
 // One-time CTA setup: weights -> shared memory (canonical layout, tf32-rounded), mbarriers, TMEM.
 __device__ __forceinline__ void setup(Smem& S, const float* __restrict__ theta) {
   const int tid = threadIdx.x;
-  for (int idx = tid; idx < kN1 * kK1; idx += blockDim.x) {
-    const int n = idx / kK1, k = idx % kK1;            // n < 64: pi unit n ; n >= 64: vf unit n - 64
-    const int t = n >> 6, j = n & 63;
+  for (int idx = tid; idx < 2 * kN1 * kK1; idx += blockDim.x) {
+    const int t = idx / (kN1 * kK1), q = idx % (kN1 * kK1);
+    const int j = q / kK1, k = q % kK1;
     const int wbase = t ? O_VF_W1 : O_PI_W1, bbase = t ? O_VF_B1 : O_PI_B1;
     const float v = (k < kObs) ? theta[wbase + j * kObs + k] : theta[bbase + j];
-    S.W1[umma_off(n, k, kK1)] = to_tf32(v);
+    S.W1[t][umma_off(j, k, kK1)] = to_tf32(v);
   }
   for (int idx = tid; idx < 2 * kN2 * kK2; idx += blockDim.x) {
     const int t = idx / (kN2 * kK2), q = idx % (kN2 * kK2);
@@ -176,23 +181,16 @@ __device__ __forceinline__ void teardown(Smem& S) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(S.tmem_base), "r"((uint32_t)kTmemCols) : "memory");
 }
 
-// Forward of both towers for the CTA's 128 envs.  Every thread of the CTA must call it (it contains
-// CTA-wide barriers); `phase` is the running mbarrier parity (0 on the first call, flipped by the callee).
-// dbg1 / dbg2 (nullable): this thread's 128 pre-activations of layer 1 / layer 2, for the unit test.
-__device__ __forceinline__ void forward(Smem& S, const float (&x)[kObs], uint32_t& phase, float (&mean)[kAct],
-                                        float& value, float* dbg1 = nullptr, float* dbg2 = nullptr) {
+// One tower for the CTA's 128 envs; every thread of the CTA must call it (CTA-wide barriers inside).
+// xv: this thread's A row of layer 1 (15 observations, tf32-rounded, and the constant 1).
+template <int NOUT>
+__device__ __forceinline__ void tower(Smem& S, const int t, const float (&xv)[16], uint32_t& phase, float (&out)[NOUT],
+                                      float* dbg1, float* dbg2) {
   const uint32_t lane_base = ((threadIdx.x >> 5) & 3) * 32;
   const uint32_t tbase = S.tmem_base + (lane_base << 16);
 
-  // ---- X -> TMEM (A operand of layer 1): 15 observations + the constant 1 that carries the bias
-  {
-    float xv[16];
-#pragma unroll
-    for (int i = 0; i < kObs; ++i) xv[i] = to_tf32(x[i]);
-    xv[15] = 1.0f;
-    tmem_st16(tbase + kColX, xv);
-    wait_st();
-  }
+  tmem_st16(tbase + kColX, xv);
+  wait_st();
   fence_before();
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -200,7 +198,7 @@ __device__ __forceinline__ void forward(Smem& S, const float (&x)[kObs], uint32_
     constexpr uint32_t idesc1 = make_idesc(kTile, kN1);
 #pragma unroll
     for (int s = 0; s < kK1 / 8; ++s) {
-      const uint64_t b = make_desc(reinterpret_cast<const char*>(S.W1) + s * 256, 128, kK1 * 32);
+      const uint64_t b = make_desc(reinterpret_cast<const char*>(S.W1[t]) + s * 256, 128, kK1 * 32);
       mma_tf32_ts(S.tmem_base + kColD1, S.tmem_base + kColX + 8 * s, b, idesc1, s > 0);
     }
     mma_commit(&S.mbar[0]);
@@ -208,7 +206,7 @@ __device__ __forceinline__ void forward(Smem& S, const float (&x)[kObs], uint32_
   mbar_wait(&S.mbar[0], phase);
   fence_after();
 
-  // ---- H1 = tanh(D1), in place: becomes the A operand of layer 2
+  // H1 = tanh(D1), in place: becomes the A operand of layer 2
 #pragma unroll
   for (int c = 0; c < kN1 / 16; ++c) {
     float v[16];
@@ -218,7 +216,7 @@ __device__ __forceinline__ void forward(Smem& S, const float (&x)[kObs], uint32_
       for (int i = 0; i < 16; ++i) dbg1[16 * c + i] = v[i];
     }
 #pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = to_tf32(tanh_mufu(v[i]));
+    for (int i = 0; i < 16; ++i) v[i] = to_tf32_fast(tanh_mufu(v[i]));
     tmem_st16(tbase + kColD1 + 16 * c, v);
   }
   wait_st();
@@ -228,12 +226,9 @@ __device__ __forceinline__ void forward(Smem& S, const float (&x)[kObs], uint32_
     fence_after();
     constexpr uint32_t idesc2 = make_idesc(kTile, kN2);
 #pragma unroll
-    for (int t = 0; t < 2; ++t) {
-#pragma unroll
-      for (int s = 0; s < kK2 / 8; ++s) {
-        const uint64_t b = make_desc(reinterpret_cast<const char*>(S.W2[t]) + s * 256, 128, kK2 * 32);
-        mma_tf32_ts(S.tmem_base + kColD2 + kN2 * t, S.tmem_base + kColD1 + kHid * t + 8 * s, b, idesc2, s > 0);
-      }
+    for (int s = 0; s < kK2 / 8; ++s) {
+      const uint64_t b = make_desc(reinterpret_cast<const char*>(S.W2[t]) + s * 256, 128, kK2 * 32);
+      mma_tf32_ts(S.tmem_base + kColD2, S.tmem_base + kColD1 + 8 * s, b, idesc2, s > 0);
     }
     mma_commit(&S.mbar[1]);
   }
@@ -241,18 +236,20 @@ __device__ __forceinline__ void forward(Smem& S, const float (&x)[kObs], uint32_
   fence_after();
   phase ^= 1;
 
-  // ---- H2 = tanh(D2 + b2) and the two heads on the CUDA cores
+  // H2 = tanh(D2 + b2) and the head on the CUDA cores
+  if constexpr (NOUT == kAct) {
 #pragma unroll
-  for (int o = 0; o < kAct; ++o) mean[o] = S.b3pi[o];
-  value = S.b3vf;
+    for (int o = 0; o < kAct; ++o) out[o] = S.b3pi[o];
+  } else {
+    out[0] = S.b3vf;
+  }
 #pragma unroll
-  for (int c = 0; c < 2 * kN2 / 16; ++c) {
+  for (int c = 0; c < kN2 / 16; ++c) {
     float v[16];
     tmem_ld16(tbase + kColD2 + 16 * c, v);
-    const int t = c >> 2, j0 = (c & 3) * 16;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const float4 b = reinterpret_cast<const float4*>(S.b2[t] + j0)[q];
+      const float4 b = reinterpret_cast<const float4*>(S.b2[t] + 16 * c)[q];
       v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
     }
     if (dbg2) {
@@ -262,17 +259,41 @@ __device__ __forceinline__ void forward(Smem& S, const float (&x)[kObs], uint32_
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       const float a = tanh_mufu(v[i]);
-      if (t == 0) {
-        const float4 w = reinterpret_cast<const float4*>(S.W3piT[j0 + i])[0];
-        mean[0] = fmaf(w.x, a, mean[0]); mean[1] = fmaf(w.y, a, mean[1]);
-        mean[2] = fmaf(w.z, a, mean[2]); mean[3] = fmaf(w.w, a, mean[3]);
+      if constexpr (NOUT == kAct) {
+        const float4 w = reinterpret_cast<const float4*>(S.W3piT[16 * c + i])[0];
+        out[0] = fmaf(w.x, a, out[0]); out[1] = fmaf(w.y, a, out[1]);
+        out[2] = fmaf(w.z, a, out[2]); out[3] = fmaf(w.w, a, out[3]);
       } else {
-        value = fmaf(S.W3vf[j0 + i], a, value);
+        out[0] = fmaf(S.W3vf[16 * c + i], a, out[0]);
       }
     }
   }
-  // the next forward's X store aliases D2: every thread only ever touches its own lane, and the MMA
-  // that wrote D2 has completed (mbarrier), so no further barrier is needed here.
+  // the next tower's X store aliases D2: a thread only ever touches its own lane, and the MMA that
+  // wrote D2 has completed (mbarrier), so no further barrier is needed here.
+}
+
+// Forward of both towers.  `phase` is the running mbarrier parity (0 before the first call).
+// dbg1 / dbg2 (nullable): this thread's 128 pre-activations (pi 0..63 | vf 64..127) of layer 1 / 2.
+__device__ __forceinline__ void forward(Smem& S, const float (&x)[kObs], uint32_t& phase, float (&mean)[kAct],
+                                        float& value, float* dbg1 = nullptr, float* dbg2 = nullptr) {
+  float xv[16];
+#pragma unroll
+  for (int i = 0; i < kObs; ++i) xv[i] = to_tf32_fast(x[i]);
+  xv[15] = 1.0f;
+  float v1[1];
+  tower<kAct>(S, 0, xv, phase, mean, dbg1, dbg2);
+  tower<1>(S, 1, xv, phase, v1, dbg1 ? dbg1 + kHid : nullptr, dbg2 ? dbg2 + kHid : nullptr);
+  value = v1[0];
+}
+
+// value tower only (the GAE bootstrap after the last step)
+__device__ __forceinline__ float forward_value(Smem& S, const float (&x)[kObs], uint32_t& phase) {
+  float xv[16], v1[1];
+#pragma unroll
+  for (int i = 0; i < kObs; ++i) xv[i] = to_tf32_fast(x[i]);
+  xv[15] = 1.0f;
+  tower<1>(S, 1, xv, phase, v1, nullptr, nullptr);
+  return v1[0];
 }
 
 }  // namespace tc
