@@ -350,7 +350,7 @@ def run_ppo(args):
     K = args.fuse
     env = drl.DroneBatch(n, drl.EnvConfig.single(), device=local, seed=args.seed, env_offset=rank * n)
     model = PPO(env, n_steps=K, batch_size=n * K // args.ppo_minibatches, n_epochs=args.ppo_epochs, seed=args.seed,
-                rollout_precision=args.precision)
+                rollout_precision=args.precision, update_precision=args.update_precision or args.precision)
 
     def one_step():
         model.collect_rollouts()
@@ -389,6 +389,7 @@ def run_ppo(args):
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": WORKLOAD_NAMES[wl], "envs_per_gpu": n, "n_steps": K, "n_epochs": args.ppo_epochs,
                            "minibatches_per_epoch": args.ppo_minibatches, "policy": "MlpPolicy 15-64-64-{4,1} tanh, random init", "rollout_precision": args.precision,
+                           "update_precision": args.update_precision or args.precision,
                            "l2": "rollout buffers %.1f GB per iteration, larger than L2" % (n * K * 93 / 1e9)},
                 "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                              "traffic": None, "note": "round-1 MLP kernels run on the fp32 CUDA cores (nominal 74.4 TFLOP/s FMA "
@@ -419,6 +420,7 @@ def main():
     ap.add_argument("--ppo-epochs", type=int, default=10)
     ap.add_argument("--ppo-minibatches", type=int, default=4)
     ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32"], help="policy MLP in the rollout: CUDA cores or tcgen05")
+    ap.add_argument("--update-precision", default=None, choices=["fp32", "tf32"], help="PPO minibatch gradient: CUDA cores or tcgen05 (default: same as --precision)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -12,6 +12,7 @@
 #include "env_handle.h"
 #include "ppo_update.cuh"
 #include "ppo_rollout_tc.cuh"
+#include "ppo_update_tc.cuh"
 
 using namespace dronecu;
 
@@ -22,11 +23,12 @@ struct dronecu_ppo {
   dronecu_ppo_config cfg;
   int device;
   int n_sm;
-  float* partials;   // [n_sm, kGradLen]
+  float* partials;   // [2 * n_sm, kGradLen] (the tensor-core kernel writes one vector per warpgroup)
   float* moments;    // [2, kParams]  Adam m | v
   double* adv_partials; // [n_sm * 8, 2]
   int64_t step;
   uint64_t launches;
+  float* dbg;        // see dronecu_ppo_debug_buffer
 };
 
 static int rollout_policy_impl(dronecu_env* e, int K, const float* d_params, int deterministic,
@@ -139,11 +141,12 @@ extern "C" int dronecu_ppo_create(const dronecu_ppo_config* cfg, int device, dro
   std::memset(p, 0, sizeof(*p));
   p->cfg = *cfg; p->device = device;
   CUDA_TRY(cudaDeviceGetAttribute(&p->n_sm, cudaDevAttrMultiProcessorCount, device));
-  CUDA_TRY(cudaMalloc(&p->partials, sizeof(float) * (size_t)p->n_sm * kGradLen));
+  CUDA_TRY(cudaMalloc(&p->partials, sizeof(float) * 2 * (size_t)p->n_sm * kGradLen));
   CUDA_TRY(cudaMalloc(&p->moments, sizeof(float) * 2 * kParams));
   CUDA_TRY(cudaMalloc(&p->adv_partials, sizeof(double) * 2 * (size_t)p->n_sm * 8));
   CUDA_TRY(cudaMemset(p->moments, 0, sizeof(float) * 2 * kParams));
   CUDA_TRY(cudaFuncSetAttribute(ppo_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UpdSmem)));
+  CUDA_TRY(cudaFuncSetAttribute(ppo_grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcUpdSmem));
   *out = p;
   return DRONECU_OK;
 }
@@ -173,10 +176,10 @@ extern "C" int dronecu_ppo_adv_stats(dronecu_ppo* p, const float* d_adv, const i
   return DRONECU_OK;
 }
 
-extern "C" int dronecu_ppo_grad(dronecu_ppo* p, const float* d_params, const float* d_obs, const float* d_actions,
-                                const float* d_old_logp, const float* d_adv, const float* d_returns,
-                                const int32_t* d_index, int64_t first, int64_t m, float adv_mean, float adv_inv_std,
-                                const double* d_adv_stats, float* d_grad, void* stream) {
+static int ppo_grad_impl(dronecu_ppo* p, const float* d_params, const float* d_obs, const float* d_actions,
+                         const float* d_old_logp, const float* d_adv, const float* d_returns,
+                         const int32_t* d_index, int64_t first, int64_t m, float adv_mean, float adv_inv_std,
+                         const double* d_adv_stats, float* d_grad, void* stream, bool tensor_cores) {
   if (!p || !d_params || !d_obs || !d_actions || !d_old_logp || !d_adv || !d_returns || !d_grad || m <= 0)
     return fail(DRONECU_ERR_INVALID, "dronecu_ppo_grad: bad argument");
   if (reinterpret_cast<uintptr_t>(d_actions) & 15) return fail(DRONECU_ERR_INVALID, "d_actions must be 16-byte aligned");
@@ -186,15 +189,45 @@ extern "C" int dronecu_ppo_grad(dronecu_ppo* p, const float* d_params, const flo
   a.adv = d_adv; a.ret = d_returns; a.index = d_index; a.first = first; a.m = m;
   a.adv_mean = adv_mean; a.adv_inv_std = adv_inv_std; a.adv_stats = d_adv_stats;
   a.clip = p->cfg.clip_range; a.vf_coef = p->cfg.vf_coef; a.ent_coef = p->cfg.ent_coef;
-  a.partials = p->partials;
+  a.partials = p->partials; a.dbg = tensor_cores ? p->dbg : nullptr;
   const int64_t tiles = (m + kUpdBlock - 1) / kUpdBlock;
-  const unsigned grid = (unsigned)std::min<int64_t>(tiles, p->n_sm);
   cudaStream_t st = (cudaStream_t)stream;
-  ppo_grad_kernel<<<grid, kUpdBlock, sizeof(UpdSmem), st>>>(a);
-  CUDA_TRY(cudaGetLastError());
-  ppo_reduce_kernel<<<(kGradLen + 255) / 256, 256, 0, st>>>(p->partials, (int)grid, d_grad);
+  if (tensor_cores) {
+    // grid (x, 2): blockIdx.y = tower; one CTA per SM, two 128-sample tiles in flight per CTA
+    const unsigned gx = (unsigned)std::max<int64_t>(1, std::min<int64_t>((tiles + tcu::kWG - 1) / tcu::kWG, p->n_sm / 2));
+    ppo_grad_tc_kernel<<<dim3(gx, 2), tcu::kThreads, kTcUpdSmem, st>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    ppo_reduce_tc_kernel<<<(kGradLen + 255) / 256, 256, 0, st>>>(p->partials, (int)gx * tcu::kWG, d_grad);
+  } else {
+    const unsigned grid = (unsigned)std::min<int64_t>(tiles, p->n_sm);
+    ppo_grad_kernel<<<grid, kUpdBlock, sizeof(UpdSmem), st>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    ppo_reduce_kernel<<<(kGradLen + 255) / 256, 256, 0, st>>>(p->partials, (int)grid, d_grad);
+  }
   CUDA_TRY(cudaGetLastError());
   p->launches += 2;
+  return DRONECU_OK;
+}
+
+extern "C" int dronecu_ppo_grad(dronecu_ppo* p, const float* d_params, const float* d_obs, const float* d_actions,
+                                const float* d_old_logp, const float* d_adv, const float* d_returns,
+                                const int32_t* d_index, int64_t first, int64_t m, float adv_mean, float adv_inv_std,
+                                const double* d_adv_stats, float* d_grad, void* stream) {
+  return ppo_grad_impl(p, d_params, d_obs, d_actions, d_old_logp, d_adv, d_returns, d_index, first, m, adv_mean,
+                       adv_inv_std, d_adv_stats, d_grad, stream, false);
+}
+
+extern "C" int dronecu_ppo_grad_tc(dronecu_ppo* p, const float* d_params, const float* d_obs, const float* d_actions,
+                                   const float* d_old_logp, const float* d_adv, const float* d_returns,
+                                   const int32_t* d_index, int64_t first, int64_t m, float adv_mean, float adv_inv_std,
+                                   const double* d_adv_stats, float* d_grad, void* stream) {
+  return ppo_grad_impl(p, d_params, d_obs, d_actions, d_old_logp, d_adv, d_returns, d_index, first, m, adv_mean,
+                       adv_inv_std, d_adv_stats, d_grad, stream, true);
+}
+
+extern "C" int dronecu_ppo_debug_buffer(dronecu_ppo* p, float* d_dbg) {
+  if (!p) return fail(DRONECU_ERR_INVALID, "null handle");
+  p->dbg = d_dbg;
   return DRONECU_OK;
 }
 

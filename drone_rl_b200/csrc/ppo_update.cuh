@@ -46,6 +46,7 @@ struct UpdArgs {
   const double* adv_stats;       // nullable: [sum, sum of squares, count] -> overrides the two scalars
   float clip, vf_coef, ent_coef;
   float* partials;           // [gridDim.x, kGradLen]
+  float* dbg;                // nullable (tensor-core kernel only): raw TMEM dump [2 gridDim.x, 128 lanes, 256 columns]
 };
 
 // forward of one tower keeping what the backward pass needs: h1 -> bufA row, h2 -> bufB row

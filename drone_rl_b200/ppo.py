@@ -98,7 +98,7 @@ class PPO:
                  gae_lambda: float = 0.95, clip_range: float = 0.2, ent_coef: float = 0.0, vf_coef: float = 0.5,
                  max_grad_norm: float = 0.5, learning_rate: float = 3e-4, normalize_advantage: bool = True,
                  seed: int = 0, device: int = 0, verbose: int = 0, policy_seed: Optional[int] = None,
-                 rollout_precision: str = "fp32"):
+                 rollout_precision: str = "fp32", update_precision: str = "fp32"):
         self.lib = _lib.load()
         self.rank, self.world = 0, 1
         if torch.distributed.is_available() and torch.distributed.is_initialized():
@@ -114,7 +114,9 @@ class PPO:
         self.verbose, self.seed = verbose, seed
         if rollout_precision not in ("fp32", "tf32"):
             raise ValueError("rollout_precision must be 'fp32' (CUDA cores, parity path) or 'tf32' (tcgen05 tensor cores)")
-        self.rollout_precision = rollout_precision
+        if update_precision not in ("fp32", "tf32"):
+            raise ValueError("update_precision must be 'fp32' (CUDA cores, parity path) or 'tf32' (tcgen05 tensor cores)")
+        self.rollout_precision, self.update_precision = rollout_precision, update_precision
         cfg = PPOConfig()
         self.lib.dronecu_ppo_config_default(C.byref(cfg))
         cfg.learning_rate, cfg.clip_range, cfg.ent_coef = learning_rate, clip_range, ent_coef
@@ -173,9 +175,10 @@ class PPO:
                 torch.distributed.all_reduce(self._adv_stats)
             stats_ptr = _ptr(self._adv_stats)
             self.launches += 2
-        _lib.check(self.lib.dronecu_ppo_grad(self._h, _ptr(self.params), _ptr(b.obs), _ptr(b.actions), _ptr(b.logp),
-                                             _ptr(b.adv), _ptr(b.ret), _ptr(index), first, m, 0.0, 1.0, stats_ptr,
-                                             _ptr(self._grad), st), "dronecu_ppo_grad")
+        grad_fn = self.lib.dronecu_ppo_grad_tc if self.update_precision == "tf32" else self.lib.dronecu_ppo_grad
+        _lib.check(grad_fn(self._h, _ptr(self.params), _ptr(b.obs), _ptr(b.actions), _ptr(b.logp),
+                           _ptr(b.adv), _ptr(b.ret), _ptr(index), first, m, 0.0, 1.0, stats_ptr,
+                           _ptr(self._grad), st), "dronecu_ppo_grad")
         if self.world > 1:
             torch.distributed.all_reduce(self._grad)      # NCCL: 42.8 KB, the only collective of the data path
         _lib.check(self.lib.dronecu_ppo_apply(self._h, _ptr(self.params), _ptr(self._grad),

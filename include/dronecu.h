@@ -257,6 +257,17 @@ int dronecu_ppo_grad(dronecu_ppo* ppo, const float* d_params, const float* d_obs
                      const float* d_old_logp, const float* d_adv, const float* d_returns, const int32_t* d_index,
                      int64_t first, int64_t m, float adv_mean, float adv_inv_std, const double* d_adv_stats,
                      float* d_grad, void* stream);
+/* Same contract on the tcgen05 tensor cores: tf32 products with fp32 accumulation, MUFU tanh; the seven
+ * matrix products of each tower run as tcgen05.mma with the weight-gradient accumulators resident in
+ * TMEM (csrc/ppo_update_tc.cuh).  Agrees with dronecu_ppo_grad to ~1e-3 of each block's largest entry. */
+int dronecu_ppo_grad_tc(dronecu_ppo* ppo, const float* d_params, const float* d_obs, const float* d_actions,
+                        const float* d_old_logp, const float* d_adv, const float* d_returns, const int32_t* d_index,
+                        int64_t first, int64_t m, float adv_mean, float adv_inv_std, const double* d_adv_stats,
+                        float* d_grad, void* stream);
+
+/* Debugging aid for dronecu_ppo_grad_tc: when d_dbg is not NULL the next calls also dump the raw TMEM image
+ * of every warpgroup, float32 [2 * grid.x, 128 lanes, 256 columns] (policy-tower CTAs; grid.x = min(ceil(tiles / 2), SMs / 2)) (grid = min(ceil(tiles / 2), SM count)). */
+int dronecu_ppo_debug_buffer(dronecu_ppo* ppo, float* d_dbg);
 
 /* clip_grad_norm_(max_grad_norm) + Adam.step() in place on d_params.  d_grad is the (all-reduced)
  * output of dronecu_ppo_grad, inv_count = 1 / (global minibatch size).  d_info (nullable) receives

@@ -91,3 +91,111 @@ def test_tc_rollout_matches_fp32_rollout_statistically(drl):
     assert torch.equal(l0[0], l1[0])                                  # log-prob depends on the noise only
     assert torch.isfinite(adv1).all()
     assert (v0 - v1).abs().mean().item() < 2e-2
+
+
+# ------------------------------------------------------------------------------------------------------
+# tensor-core minibatch gradient (csrc/ppo_update_tc.cuh)
+# ------------------------------------------------------------------------------------------------------
+def _grad(model, index, m, first=0, tc=True):
+    import ctypes as C
+    from drone_rl_b200 import _lib
+    b = model.buf
+    P = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+    model._adv_stats.zero_()
+    _lib.check(model.lib.dronecu_ppo_adv_stats(model._h, P(b.adv), P(index), first, m, P(model._adv_stats), None))
+    fn = model.lib.dronecu_ppo_grad_tc if tc else model.lib.dronecu_ppo_grad
+    _lib.check(fn(model._h, P(model.params), P(b.obs), P(b.actions), P(b.logp), P(b.adv), P(b.ret), P(index), first, m,
+                  0.0, 1.0, P(model._adv_stats), P(model._grad), None))
+    torch.cuda.synchronize()
+    return model._grad.cpu().double().numpy().copy()
+
+
+def _separated_buffers(model, seed):
+    """Like tests/test_gpu_ppo._fake_buffers, but the old log-probs sit at offsets {-0.45, -0.08, 0, 0.07,
+    0.4} (+- 0.01) from the current policy's: ratios of 1.57 / 1.08 / 1 / 0.93 / 0.67 exercise both sides
+    of the clip, and no sample lies within the tf32 forward error of the 0.8 / 1.2 boundaries -- the clipped
+    objective's gradient is discontinuous there, so a borderline sample would make ANY reduced-precision
+    forward differ from float64 by that sample's whole gradient (measured with the unseparated buffers:
+    1-2 % of the samples flip, 5 % error on the policy blocks, value blocks unaffected)."""
+    b = model.buf
+    K, n = b.obs.shape[0], b.obs.shape[1]
+    g = torch.Generator().manual_seed(seed)
+    obs = torch.randn(K, n, 15, generator=g) * 2.0
+    theta = model.params.cpu().double()
+    mean, value, log_std = po.forward(theta, obs.double().reshape(-1, 15))
+    act = mean + torch.exp(log_std) * torch.randn(K * n, 4, generator=g, dtype=torch.float64)
+    offs = torch.tensor([-0.45, -0.08, 0.0, 0.07, 0.4], dtype=torch.float64)[torch.randint(0, 5, (K * n,), generator=g)]
+    old_logp = po.log_prob(mean, log_std, act) + offs + 0.01 * torch.randn(K * n, generator=g, dtype=torch.float64)
+    adv = torch.randn(K * n, generator=g, dtype=torch.float64) * 3 + 0.5
+    # a biased value function: with ret - value pure noise the reference gradient is a sqrt(m)-sized noise sum
+    # while the tf32 forward error of the value adds coherently (~ m * 1e-3): the relative error would grow
+    # like sqrt(m) without saying anything about the kernel
+    ret = value + 0.7 + torch.randn(K * n, generator=g, dtype=torch.float64)
+    b.obs.copy_(obs.cuda()); b.actions.copy_(act.float().reshape(K, n, 4).cuda())
+    b.logp.copy_(old_logp.float().reshape(K, n).cuda()); b.adv.copy_(adv.float().reshape(K, n).cuda())
+    b.ret.copy_(ret.float().reshape(K, n).cuda())
+    torch.cuda.synchronize()
+    f64 = lambda t: t.cpu().double()
+    return (f64(b.obs).reshape(-1, 15), f64(b.actions).reshape(-1, 4), f64(b.logp).reshape(-1),
+            f64(b.adv).reshape(-1), f64(b.ret).reshape(-1))
+
+
+@pytest.mark.parametrize("m", [128, 1000, 128 * 300 + 37, 128 * 2 * 148 * 3])
+def test_tc_minibatch_gradient(drl, m):
+    """tf32 tensor-core gradient vs float64 autograd of the oracle loss (and vs the fp32 CUDA-core kernel).
+    Stated tolerance: every parameter block within 1e-2 of its own largest entry (tf32 operands carry
+    2^-11 relative rounding, MUFU tanh 2^-11; the sum over m samples averages part of it out), whole
+    vector within 5e-3 of the largest entry; statistics as for the fp32 kernel but rtol 5e-3."""
+    from tests.test_gpu_ppo import _rand_params
+    from drone_rl_b200.ppo import PPO
+    n, K = 1024, (m + 1023) // 1024 + 1
+    model = PPO(n, n_steps=K, ent_coef=0.01)
+    model.params.copy_(_rand_params(9, 0.5).float().cuda())
+    obs, act, old_logp, adv, ret = _separated_buffers(model, 4)
+    B = obs.shape[0]
+    idx = torch.randperm(B, generator=torch.Generator().manual_seed(1))[:m]
+    g = _grad(model, idx.to(torch.int32).cuda(), m, tc=True)
+    g32 = _grad(model, idx.to(torch.int32).cuda(), m, tc=False)
+    theta = model.params.cpu().double().requires_grad_(True)
+    loss, stats = po.ppo_loss(theta, obs[idx], act[idx], old_logp[idx], adv[idx], ret[idx], ent_coef=0.01)
+    (ref,) = torch.autograd.grad(loss, theta)
+    ref = ref.numpy() * m
+    scale = np.abs(ref).max()
+    report, bad = [], []
+    for name, (off, shape) in po.offsets().items():
+        k = int(np.prod(shape))
+        blk_ref, blk = ref[off:off + k], g[off:off + k]
+        e = np.abs(blk - blk_ref).max() / max(np.abs(blk_ref).max(), 1e-3 * scale)
+        e32 = np.abs(blk - g32[off:off + k]).max() / max(np.abs(blk_ref).max(), 1e-3 * scale)
+        report.append(f"{name} {e:.2e} (vs fp32 kernel {e32:.2e})")
+        if not e <= 1e-2:
+            bad.append(name)
+    print(f"m={m}: " + "; ".join(report))
+    assert not bad, f"blocks out of tolerance: {bad}: " + "; ".join(report)
+    assert np.abs(g[:po.N_PARAMS] - ref).max() <= 5e-3 * scale
+    st = g[po.N_PARAMS:]
+    assert st[4] == m
+    np.testing.assert_allclose(st[0] / m, stats["policy_gradient_loss"], rtol=5e-3, atol=1e-4)
+    np.testing.assert_allclose(st[1] / m, stats["value_loss"], rtol=5e-3)
+    np.testing.assert_allclose(st[3] / m, stats["clip_fraction"], atol=2.0 / m)
+    assert 0.2 < stats["clip_fraction"] < 0.6
+    again = _grad(model, idx.to(torch.int32).cuda(), m, tc=True)
+    assert np.array_equal(g, again)                       # fixed tile order + fixed-order reduction
+    model.close()
+
+
+def test_tc_update_trains_like_fp32(drl):
+    """A few PPO iterations with the tf32 update track the fp32 update (same seeds, same rollouts at
+    iteration 0): parameters stay within 2e-3 after the first 8 optimiser steps."""
+    from drone_rl_b200.ppo import PPO
+    ps = []
+    for prec in ("fp32", "tf32"):
+        m = PPO(drl.DroneBatch(2048, drl.EnvConfig.single(), seed=3), n_steps=16, batch_size=8192, n_epochs=2, seed=3,
+                update_precision=prec)
+        m.collect_rollouts()
+        m.train()
+        torch.cuda.synchronize()
+        assert torch.isfinite(m.params).all()
+        ps.append(m.params.clone())
+        m.close()
+    assert (ps[0] - ps[1]).abs().max().item() < 2e-3
