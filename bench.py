@@ -157,6 +157,8 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
+    if args.workload in ("c3", "c5"):
+        return run_reference_ppo(args, cores)
     k_inner = 8
     cb = CpuBaseline(cores)
     for _ in range(max(1, args.warmup)):
@@ -171,6 +173,56 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "env_steps_per_sec", "value": v, "unit": "env-steps/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD_NAMES[args.workload], "sample": sample},
+            "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+PPO_CPU_SAMPLE = dict(n_envs=4096, n_steps=32, n_epochs=10, minibatches=4)
+
+
+def time_cpu_ppo(update, budget_s=10.0):
+    """The restated-SB3 CPU loop (oracle/ppo_loop.py, torch CPU with all host threads + the numpy env port):
+    (a) batched the way this repo's workload is, (b) exactly as the reference runs it (train.py:33-43:
+    one env, n_steps 2048, batch 64, 10 epochs)."""
+    import torch
+    from oracle import ppo_loop
+    c = PPO_CPU_SAMPLE
+    v, its, dt = ppo_loop.time_loop(c["n_envs"], c["n_steps"], c["n_envs"] * c["n_steps"] // c["minibatches"],
+                                    c["n_epochs"], budget_s=budget_s, update=update)
+    sample = (f"restated SB3 loop on CPU (torch {torch.get_num_threads()} threads + numpy env port): {c['n_envs']} envs x "
+              f"{c['n_steps']} steps" + (f", {c['n_epochs']} epochs x {c['minibatches']} minibatches" if update else ", rollout only") +
+              f"; {its} iterations in {dt:.1f}s")
+    if update:
+        v1, its1, dt1 = ppo_loop.time_loop(1, 2048, 64, 10, budget_s=budget_s, update=True)
+        sample += f" | reference's own config (1 env, n_steps 2048, batch 64, 10 epochs): {v1:.0f} env-steps/s"
+    return v, sample
+
+
+def run_reference_ppo(args, cores):
+    from oracle import ppo_loop
+    c = PPO_CPU_SAMPLE
+    update = args.workload == "c5"
+    loop = ppo_loop.PPOLoopOracle(c["n_envs"], c["n_steps"], c["n_envs"] * c["n_steps"] // c["minibatches"], c["n_epochs"])
+
+    def one():
+        loop.collect_rollouts()
+        if update:
+            loop.train()
+    for _ in range(max(1, args.warmup)):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        one()
+    dt = time.perf_counter() - t0
+    v = args.steps * c["n_envs"] * c["n_steps"] / dt
+    sample = (f"restated SB3 loop on CPU (torch, all host threads + numpy env port): {c['n_envs']} envs x {c['n_steps']} steps per "
+              f"bench step" + (f", {c['n_epochs']} epochs x {c['minibatches']} minibatches" if update else ", rollout only"))
+    line = {"impl": "reference", "metric": "env_steps_per_sec", "value": v, "unit": "env-steps/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD_NAMES[args.workload], "sample": sample},
             "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -383,6 +435,34 @@ def run_ppo(args):
     pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.isfile(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
     peak = float(pk.get("bf16_tflops_sustained", 1400.0))
     achieved = value / world * flop_per_step / 1e12
+    tensor = (args.precision == "tf32") and (wl == "c3" or (args.update_precision or args.precision) == "tf32")
+
+    # ---- e2e: the public API (PPO.collect_rollouts / PPO.learn), wall clock, every iteration reads its
+    # result (episode statistics + train/* scalars) back to the host.  The simulator lives on the GPU, so an
+    # iteration has no host input: h2d is 0 by construction.
+    e2e = None
+    if not args.no_e2e:
+        its = max(1, min(args.steps, 5))
+        barrier()
+        t0 = time.perf_counter()
+        if wl == "c5":
+            model.num_timesteps = 0
+            model.learn(total_timesteps=its * n * K * world)
+            d2h = 9 * 4 + 128 * 64
+        else:
+            for _ in range(its):
+                model.collect_rollouts()
+                st = env.episode_stats(reset=True)
+            d2h = 128 * 64
+        barrier()
+        dt = time.perf_counter() - t0
+        td = torch.tensor([dt], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(td, op=dist.ReduceOp.MAX)
+        e2e = {"value": its * n * K * world / float(td.item()), "unit": "env-steps/s", "h2d_bytes_per_step": 0,
+               "d2h_bytes_per_step": d2h, "api": "PPO.learn" if wl == "c5" else "PPO.collect_rollouts + episode_stats",
+               "iterations": its, "note": "GPU-resident simulator: no host inputs per iteration; the result read back is the "
+               "episode statistics (128 slots x 64 B)" + (" and the train/* scalars" if wl == "c5" else "")}
     if rank == 0:
         line = {"metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -392,11 +472,15 @@ def run_ppo(args):
                            "update_precision": args.update_precision or args.precision,
                            "l2": "rollout buffers %.1f GB per iteration, larger than L2" % (n * K * 93 / 1e9)},
                 "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                             "traffic": None, "note": "round-1 MLP kernels run on the fp32 CUDA cores (nominal 74.4 TFLOP/s FMA "
-                             "peak: frac_of_fp32 = %.3f); the denominator is the measured bf16 tensor peak" % (achieved / 74.4),
+                             "traffic": None, "note": ("tcgen05 kind::tf32 MMAs (tf32 dense peak = half the bf16 peak used as the "
+                             "denominator)" if tensor else "fp32 CUDA-core parity path (nominal 74.4 TFLOP/s FMA peak: frac_of_fp32 = "
+                             "%.3f); the denominator is the measured bf16 tensor peak" % (achieved / 74.4)),
                              "flop_per_env_step": flop_per_step},
-                "e2e": None, "gpu_launches": int(launches), "clocks": clocks.summary(),
+                "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks.summary(),
                 "train": {k: v for k, v in model.logger_values.items() if k.startswith("train/")}}
+        if world == 1 and not args.no_cpu:
+            v, sample = time_cpu_ppo(update=(wl == "c5"))
+            line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": os.cpu_count() or 1, "kind": "port", "sample": sample}
         print(json.dumps(line), flush=True)
     model.close()
     if world > 1:
@@ -419,7 +503,7 @@ def main():
     ap.add_argument("--ppo-envs", type=int, default=1_048_576)
     ap.add_argument("--ppo-epochs", type=int, default=10)
     ap.add_argument("--ppo-minibatches", type=int, default=4)
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32"], help="policy MLP in the rollout: CUDA cores or tcgen05")
+    ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32"], help="policy MLP in the rollout: CUDA cores or tcgen05")
     ap.add_argument("--update-precision", default=None, choices=["fp32", "tf32"], help="PPO minibatch gradient: CUDA cores or tcgen05 (default: same as --precision)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
