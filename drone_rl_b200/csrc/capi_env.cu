@@ -78,6 +78,7 @@ static EnvParams digest(const dronecu_config& c, uint64_t seed, int64_t env_offs
   P.inv_curriculum_period = (float)(1.0 / (double)c.curriculum_period);
   P.r_max_sq = (float)(c.r_max * c.r_max);
   P.seed = seed;
+  philox_expand_key(seed, P.keys);
   P.env_offset = (uint64_t)env_offset;
   return P;
 }
@@ -137,7 +138,7 @@ extern "C" int dronecu_create(const dronecu_config* cfg, int device, int64_t n_e
   if (cfg->obs_dim != 12 && cfg->obs_dim != 15) return fail(DRONECU_ERR_INVALID, "obs_dim must be 12 or 15");
   if (cfg->max_steps <= 0 || cfg->curriculum_period <= 0 || !(cfg->mass > 0) || !(cfg->dt > 0))
     return fail(DRONECU_ERR_INVALID, "dronecu_create: non-positive max_steps/curriculum_period/mass/dt");
-  if (n_envs > ((int64_t)1 << 31) * (int64_t)kBlock / 2) return fail(DRONECU_ERR_INVALID, "n_envs too large");
+  if (n_envs > ((int64_t)1 << 30)) return fail(DRONECU_ERR_INVALID, "n_envs too large (at most 2^30 envs per handle: 32-bit thread indices)");
   int ndev = 0;
   cudaError_t err = cudaGetDeviceCount(&ndev);
   if (err != cudaSuccess || ndev == 0) {

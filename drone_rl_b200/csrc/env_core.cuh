@@ -29,6 +29,7 @@ struct EnvParams {
   int32_t curriculum_period, max_steps;
   float inv_curriculum_period, r_max_sq;
   uint64_t seed, env_offset;
+  PhiloxKeys keys;   // round keys of `seed`
 };
 
 struct EnvState {
@@ -101,7 +102,7 @@ __device__ __forceinline__ void reset_env(EnvState& s, const EnvParams& P, uint6
   if constexpr (RANDOMIZED) {
     // exactly five uniforms, in the reference's order pos.x pos.y tgt.x tgt.y tgt.z (drone.py:57,73),
     // out of ONE Philox call: 4 x 24 high bits + the 3 low bytes of words 0..2 (oracle/philox.py)
-    const uint4 w = env_stream(P.seed, env_id, (uint64_t)(uint32_t)s.ep_num, STREAM_RESET);
+    const uint4 w = env_stream(P.keys, env_id, (uint64_t)(uint32_t)s.ep_num, STREAM_RESET);
     s.px = u01(w.x) - 0.5f;   // exact: u is a multiple of 2^-24
     s.py = u01(w.y) - 0.5f;
     s.pz = P.start_z;
@@ -134,6 +135,57 @@ __device__ __forceinline__ void reset_env(EnvState& s, const EnvParams& P, uint6
 // ---------------------------------------------------------------------------------------------
 // one physics step + reward + termination flags.  drone.py:101-157 / vectorized_drone.py:151-213
 // ---------------------------------------------------------------------------------------------
+// sin and cos of the three Euler angles.  One range check for all three (the reference never wraps its
+// angles, so huge arguments must stay exact: they take libm's Payne-Hanek path, as do inf -> NaN); the common
+// case is a three-term Cody-Waite reduction by pi/2 (valid below 105615, as in CUDA's own sincosf) with the
+// quadrant taken from the low mantissa bits of a magic-number rounding, and the Cephes single-precision
+// minimax polynomials on [-pi/4, pi/4] (< 1.5 ulp).  NaN arguments fall through the check (fmaxf drops
+// NaN) and propagate through the arithmetic.
+__device__ __forceinline__ void sincos_reduced(float x, float& s, float& c) {
+  const float j = fmaf(x, 0.636619772367581343f, 12582912.0f);      // 1.5 * 2^23: round to nearest integer
+  const uint32_t q = __float_as_uint(j);
+  const float n = j - 12582912.0f;
+  float r = fmaf(n, -1.5707962512969970703f, x);
+  r = fmaf(n, -7.5497894158615963534e-08f, r);
+  r = fmaf(n, -5.3903029534742383927e-15f, r);
+  const float r2 = r * r;
+  float ps = fmaf(r2, -1.9515295891e-4f, 8.3321608736e-3f);
+  ps = fmaf(ps, r2, -1.6666654611e-1f);
+  const float sn = fmaf(ps, r2 * r, r);
+  float pc = fmaf(r2, 2.443315711809948e-5f, -1.388731625493765e-3f);
+  pc = fmaf(pc, r2, 4.166664568298827e-2f);
+  pc = fmaf(pc, r2, -0.5f);
+  const float cs = fmaf(pc, r2, 1.0f);
+  const bool odd = q & 1u;
+  const float s0 = odd ? cs : sn, c0 = odd ? sn : cs;
+  s = __uint_as_float(__float_as_uint(s0) ^ ((q << 30) & 0x80000000u));          // quadrants 2, 3: sin < 0
+  c = __uint_as_float(__float_as_uint(c0) ^ (((q + 1u) << 30) & 0x80000000u));   // quadrants 1, 2: cos < 0
+}
+
+__device__ __forceinline__ void sincos3(float a, float b, float g, float& sa, float& ca, float& sb, float& cb,
+                                        float& sg, float& cg) {
+  if (fmaxf(fmaxf(fabsf(a), fabsf(b)), fabsf(g)) < 105615.0f) {
+    sincos_reduced(a, sa, ca);
+    sincos_reduced(b, sb, cb);
+    sincos_reduced(g, sg, cg);
+  } else {
+    sincosf(a, &sa, &ca);
+    sincosf(b, &sb, &cb);
+    sincosf(g, &sg, &cg);
+  }
+}
+
+__device__ __forceinline__ float rcp_approx(float x) {     // 1 ulp; 0 -> inf, inf -> 0, NaN -> NaN like 1.0f / x
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sqrt_approx(float x) {    // 1 ulp; 0 -> 0, inf -> inf, NaN -> NaN like sqrtf
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 struct StepResult {
   float reward;
   bool crashed;   // z < z_floor or |pos| > r_max          (drone.py:154)
@@ -148,9 +200,7 @@ __device__ __forceinline__ StepResult step_env(EnvState& s, const EnvParams& P, 
   const float tau_yaw = P.k_yaw * (((f.x - f.y) + f.z) - f.w);
 
   float sr, cr, sp, cp, sy, cy;
-  sincosf(s.roll, &sr, &cr);    // accurate (Payne-Hanek for huge args): the reference never wraps angles
-  sincosf(s.pitch, &sp, &cp);
-  sincosf(s.yaw, &sy, &cy);
+  sincos3(s.roll, s.pitch, s.yaw, sr, cr, sp, cp, sy, cy);
 
   // third column of R = Rz Ry Rx (drone.py:170-172) times thrust / mass, plus gravity (drone.py:124)
   const float tm = thrust * P.inv_mass;
@@ -159,7 +209,7 @@ __device__ __forceinline__ StepResult step_env(EnvState& s, const EnvParams& P, 
   const float az = -P.gravity + (cp * cr) * tm;
 
   // Euler rates from the OLD angles and OLD body rates (drone.py:131, :181-186)
-  const float sec_p = 1.0f / cp;
+  const float sec_p = rcp_approx(cp);
   const float tan_p = sp * sec_p;
   const float roll_dot = s.wp + (sr * tan_p) * s.wq + (cr * tan_p) * s.wr;
   const float pitch_dot = 0.0f * s.wp + cr * s.wq + (-sr) * s.wr;
@@ -178,7 +228,7 @@ __device__ __forceinline__ StepResult step_env(EnvState& s, const EnvParams& P, 
 
   // reward (drone.py:142-148) and termination (drone.py:154-157); NaN compares false
   const float dx = s.px - s.tx, dy = s.py - s.ty, dz = s.pz - s.tz;
-  const float dist = sqrtf(dx * dx + dy * dy + dz * dz);
+  const float dist = sqrt_approx(dx * dx + dy * dy + dz * dz);
   StepResult r;
   r.reward = -P.reward_scale * dist;
   if (dist < P.bonus_radius) r.reward += P.bonus;

@@ -11,7 +11,10 @@
 
 namespace dronecu {
 
-constexpr int kBlock = 256;
+#ifndef DRONECU_BLOCK
+#define DRONECU_BLOCK 256
+#endif
+constexpr int kBlock = DRONECU_BLOCK;
 constexpr int kWarps = kBlock / 32;
 constexpr int kStatSlots = 128;   // episode statistics are spread over this many L2 lines
 
@@ -48,7 +51,8 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 #define DRONECU_EMIT_BULK 0
 #endif
 #ifndef DRONECU_MIN_BLOCKS
-#define DRONECU_MIN_BLOCKS 4   // <= 64 registers/thread: 4 CTAs of 256 threads per SM (ncu: round-1 notes)
+#define DRONECU_MIN_BLOCKS 3   // <= 80 registers/thread, 3 CTAs of 256 threads per SM: no spills and no per-step
+                               // re-derivation of indices (at 64 registers ptxas did both); A/B in profiles/README.md
 #endif
 
 // One warp's 32 observations: registers -> per-warp smem tile (stride D words) -> global as
@@ -104,61 +108,57 @@ __device__ __forceinline__ bool emit_fast_ok(const float* base, int64_t warp_bas
 // RECORD = true: the "rollout record" output set -- next_obs, reward, done (and the applied action
 // when it is generated in-kernel) are all present, nothing else is: no per-step null checks.
 // RECORD = false: every output pointer is optional (the VecEnv.step boundary with its info arrays).
+//
+// Register diet (ncu, round 1: at 64 registers ptxas re-derived thread ids / pointers every step, ~50 of
+// 452 warp-instructions per env-step): the thread index is 32-bit (n <= 2^30, checked by the host), the
+// per-step output bases are warp-uniform (k * n lives in the uniform datapath) so no per-thread running
+// pointers exist, and the episode statistics go straight to shared-memory atomics on the done path.
 template <int OBS_DIM, bool RANDOMIZED, bool AUTORESET, int ACT_MODE, bool RECORD>
 __global__ void __launch_bounds__(kBlock, DRONECU_MIN_BLOCKS) rollout_kernel(const __grid_constant__ RolloutArgs A) {
   __shared__ __align__(128) float tiles[kWarps][32 * OBS_DIM];
-  __shared__ unsigned long long blk_stats[3];
+  __shared__ uint32_t blk_stats[3];      // episodes, terminated, length sum of this CTA (<= 256 * K each)
   __shared__ double blk_ret;
 
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t warp_base = (int64_t)blockIdx.x * blockDim.x + warp * 32;
-  const int64_t i = warp_base + lane;
-  const bool active = i < A.n;
-  const int valid = (int)max((int64_t)0, min((int64_t)32, A.n - warp_base));
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t warp_base = i - lane;
+  const uint32_t n32 = (uint32_t)A.n;
+  const bool active = i < n32;
+  const int valid = (warp_base >= n32) ? 0 : (int)min(32u, n32 - warp_base);
   float* tile = tiles[warp];
   const EnvParams& P = A.P;
-  const uint64_t env_id = P.env_offset + (uint64_t)i;
 
   if (threadIdx.x < 3) blk_stats[threadIdx.x] = 0;
   if (threadIdx.x == 3) blk_ret = 0.0;
+  __syncthreads();
+  float ret_sum = 0.f;                   // returns of the episodes this thread finished (exact float32 values)
 
   EnvState s = {};
   if (active) s = load_state(A.state, i);
 
   if (A.obs0 != nullptr && valid > 0)
-    emit_obs_rows<OBS_DIM>(tile, A.obs0 + warp_base * OBS_DIM, s, lane, valid, active,
+    emit_obs_rows<OBS_DIM>(tile, A.obs0 + (size_t)warp_base * OBS_DIM, s, lane, valid, active,
                            emit_fast_ok<OBS_DIM>(A.obs0, warp_base, A.n, valid));
 
-  uint32_t n_done = 0, n_term = 0, len_sum = 0;
-  float ret_sum = 0.f;
   const bool fast_obs = emit_fast_ok<OBS_DIM>(A.next_obs, warp_base, A.n, valid);
-
-  // running output pointers: one 64-bit add per output per step instead of k*n + i each time
-  const int64_t n = A.n;
-  const float4* p_act_in = A.actions + i;
-  float4* p_act_out = A.out_actions + i;
-  float* p_rew = A.reward + i;
-  uint8_t* p_done = A.done + i;
-  uint8_t* p_trunc = A.truncated + i;
-  float* p_obs = A.next_obs + warp_base * OBS_DIM;
-  int64_t row = 0;                                   // only used by the rare "where done" outputs
   const bool w_act = RECORD ? (ACT_MODE == 1) : (A.out_actions != nullptr);
   const bool w_rew = RECORD || (A.reward != nullptr);
   const bool w_done = RECORD || (A.done != nullptr);
   const bool w_trunc = !RECORD && (A.truncated != nullptr);
   const bool w_obs = RECORD || (A.next_obs != nullptr);
   const float act_scale = P.motor_max * 5.9604644775390625e-8f;   // exact: a power of two times motor_max
+  const size_t n = (size_t)A.n;
 
   float4 act = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (ACT_MODE == 0 && active) act = ld_quad_nc(p_act_in);
+  if (ACT_MODE == 0 && active) act = ld_quad_nc(A.actions + i);
 
-  for (int k = 0; k < A.K; ++k) {
+  size_t koff = 0;                                   // k * n: uniform, the base of step k in every [K,n,...] output
+  for (int k = 0; k < A.K; ++k, koff += n) {
     float4 f = act;
     if constexpr (ACT_MODE == 0) {
-      p_act_in += n;
-      if (active && k + 1 < A.K) act = ld_quad_nc(p_act_in);     // software prefetch of the next quad
+      if (active && k + 1 < A.K) act = ld_quad_nc(A.actions + koff + n + i);     // software prefetch of the next quad
     } else {
-      const uint4 w = env_stream(P.seed, env_id, A.t0 + (uint64_t)k, STREAM_ACTION);
+      const uint4 w = env_stream(P.keys, P.env_offset + (uint64_t)i, A.t0 + (uint64_t)k, STREAM_ACTION);
       f = make_float4((float)(w.x >> 8) * act_scale, (float)(w.y >> 8) * act_scale,
                       (float)(w.z >> 8) * act_scale, (float)(w.w >> 8) * act_scale);
     }
@@ -166,56 +166,47 @@ __global__ void __launch_bounds__(kBlock, DRONECU_MIN_BLOCKS) rollout_kernel(con
     const bool done = r.crashed || r.timeout;
 
     if (active) {
-      if (w_act) st_quad(p_act_out, f);
-      if (w_rew) *p_rew = r.reward;
-      if (w_done) *p_done = done ? 1 : 0;
-      if (w_trunc) *p_trunc = (r.timeout && !r.crashed) ? 1 : 0;
+      if (w_act) st_quad(A.out_actions + koff + i, f);
+      if (w_rew) (A.reward + koff)[i] = r.reward;
+      if (w_done) (A.done + koff)[i] = done ? 1 : 0;
+      if (w_trunc) (A.truncated + koff)[i] = (r.timeout && !r.crashed) ? 1 : 0;
       if (done) {
-        n_done += 1;
-        n_term += r.crashed ? 1 : 0;
-        len_sum += (uint32_t)s.ep_len;
+        atomicAdd(&blk_stats[0], 1u);
+        if (r.crashed) atomicAdd(&blk_stats[1], 1u);
+        atomicAdd(&blk_stats[2], (uint32_t)s.ep_len);
         ret_sum += s.ep_ret;
         if constexpr (!RECORD) {
-          if (A.terminal_obs != nullptr) write_obs<OBS_DIM>(A.terminal_obs + (row + i) * OBS_DIM, s);
-          if (A.episode_r != nullptr) A.episode_r[row + i] = s.ep_ret;
-          if (A.episode_l != nullptr) A.episode_l[row + i] = s.ep_len;
+          if (A.terminal_obs != nullptr) write_obs<OBS_DIM>(A.terminal_obs + (koff + i) * OBS_DIM, s);
+          if (A.episode_r != nullptr) A.episode_r[koff + i] = s.ep_ret;
+          if (A.episode_l != nullptr) A.episode_l[koff + i] = s.ep_len;
         }
         if constexpr (AUTORESET) {
-          reset_env<RANDOMIZED>(s, P, env_id);
+          reset_env<RANDOMIZED>(s, P, P.env_offset + (uint64_t)i);
         } else {
           s.ep_ret = 0.f;   // VecMonitor zeroes its accumulators on done even without a reset
           s.ep_len = 0;
         }
       }
     }
-    if (w_obs && valid > 0) emit_obs_rows<OBS_DIM>(tile, p_obs, s, lane, valid, active, fast_obs);
-    p_act_out += n; p_rew += n; p_done += n; p_trunc += n; p_obs += n * OBS_DIM; row += n;
+    if (w_obs && valid > 0)
+      emit_obs_rows<OBS_DIM>(tile, A.next_obs + (koff + warp_base) * OBS_DIM, s, lane, valid, active, fast_obs);
   }
 
   if (active) store_state(A.state, i, s);
 
-  // episode statistics: warp shuffle -> block smem -> one atomic set per CTA into a hashed slot
-  __syncthreads();   // blk_stats initialised
-  if (__ballot_sync(0xffffffffu, n_done != 0)) {
-    n_done = __reduce_add_sync(0xffffffffu, n_done);
-    n_term = __reduce_add_sync(0xffffffffu, n_term);
-    len_sum = __reduce_add_sync(0xffffffffu, len_sum);
+  // episode statistics: warp shuffle (returns) -> block smem -> one atomic set per CTA into a hashed slot
+  if (__ballot_sync(0xffffffffu, ret_sum != 0.f)) {
     double rs = (double)ret_sum;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, o);
-    if (lane == 0) {
-      atomicAdd(&blk_stats[0], (unsigned long long)n_done);
-      atomicAdd(&blk_stats[1], (unsigned long long)n_term);
-      atomicAdd(&blk_stats[2], (unsigned long long)len_sum);
-      atomicAdd(&blk_ret, rs);
-    }
+    if (lane == 0) atomicAdd(&blk_ret, rs);
   }
   __syncthreads();
   if (threadIdx.x == 0 && blk_stats[0] != 0) {
     StatSlot* slot = A.stats + (blockIdx.x % kStatSlots);
-    atomicAdd(&slot->episodes, blk_stats[0]);
-    atomicAdd(&slot->terminated, blk_stats[1]);
-    atomicAdd(&slot->length_sum, blk_stats[2]);
+    atomicAdd(&slot->episodes, (unsigned long long)blk_stats[0]);
+    atomicAdd(&slot->terminated, (unsigned long long)blk_stats[1]);
+    atomicAdd(&slot->length_sum, (unsigned long long)blk_stats[2]);
     atomicAdd(&slot->return_sum, blk_ret);
   }
 #if DRONECU_EMIT_BULK

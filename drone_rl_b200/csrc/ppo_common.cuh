@@ -31,8 +31,8 @@ __device__ __forceinline__ float tanh_fast(float x) {
 // four standard normals from the NOISE stream (oracle/philox.py noise_normals):
 // z0 = r(u0) cos(2 pi u1), z1 = r(u0) sin(2 pi u1), z2 = r(u2) cos(2 pi u3), z3 = r(u2) sin(2 pi u3),
 // r(u) = sqrt(-2 ln(u + 2^-24))
-__device__ __forceinline__ float4 noise_normals(uint64_t seed, uint64_t env_id, uint64_t t) {
-  const uint4 w = env_stream(seed, env_id, t, STREAM_NOISE);
+__device__ __forceinline__ float4 noise_normals(const PhiloxKeys& keys, uint64_t env_id, uint64_t t) {
+  const uint4 w = env_stream(keys, env_id, t, STREAM_NOISE);
   const float r0 = sqrtf(-2.0f * logf(u01(w.x) + 5.9604644775390625e-8f));
   const float r1 = sqrtf(-2.0f * logf(u01(w.z) + 5.9604644775390625e-8f));
   float s0, c0, s1, c1;

@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(kPolBlock) policy_rollout_kernel(const __grid_
       a = make_float4(mean[0], mean[1], mean[2], mean[3]);
       logp = -logstd_sum - kAct * kHalfLog2Pi;
     } else {
-      const float4 z = noise_normals(P.seed, env_id, A.t0 + (uint64_t)k);
+      const float4 z = noise_normals(P.keys, env_id, A.t0 + (uint64_t)k);
       a = make_float4(fmaf(std_[0], z.x, mean[0]), fmaf(std_[1], z.y, mean[1]),
                       fmaf(std_[2], z.z, mean[2]), fmaf(std_[3], z.w, mean[3]));
       // Normal(mean, std).log_prob(a) summed over the 4 dims; (a - mean) / std == z up to rounding
