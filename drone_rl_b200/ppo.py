@@ -276,11 +276,45 @@ class PPO:
             self.batch.global_step = sd.get("env_global_step", self.batch.global_step)
 
     def save(self, path: str):
-        torch.save(self.state_dict(), path if path.endswith((".pt", ".zip")) else path + ".pt")
+        """SB3 ``model.save(path)`` (train.py:70): no suffix -> ``path + ".zip"``, an archive in SB3's layout
+        (sb3_zip.py) that also carries the env / curriculum / RNG state; ``.pt`` -> a plain torch checkpoint."""
+        if path.endswith(".pt"):
+            torch.save(self.state_dict(), path)
+            return
+        from . import sb3_zip
+        sd = self.state_dict()
+        hyper = {"n_steps": self.n_steps, "batch_size": self.batch_size, "n_epochs": self.n_epochs, "gamma": self.gamma,
+                 "gae_lambda": self.gae_lambda, "learning_rate": float(self.cfg.learning_rate),
+                 "clip_range": float(self.cfg.clip_range), "ent_coef": float(self.cfg.ent_coef),
+                 "vf_coef": float(self.cfg.vf_coef), "max_grad_norm": float(self.cfg.max_grad_norm),
+                 "n_envs": self.n_envs, "num_timesteps": self.num_timesteps, "_n_updates": self.n_updates, "seed": self.seed}
+        extra = {k: sd[k] for k in ("num_timesteps", "n_updates", "env_state", "env_global_step")}
+        sb3_zip.export_zip(path if path.endswith(".zip") else path + ".zip", sd["params"], sd["adam"], sd["adam_step"],
+                           hyper, extra)
 
     @classmethod
     def load(cls, path: str, env=1, **kw):
-        sd = torch.load(path, weights_only=False)
+        """SB3 ``PPO.load(path, env, **overrides)`` (train.py:22-30, test.py:7): a ``.zip`` written by this class or by
+        stable-baselines3 itself (policy + Adam state; hyper-parameters stored in the archive are defaults that
+        keyword arguments override), or a ``.pt`` checkpoint."""
+        import os
+        if not path.endswith((".pt", ".zip")) and os.path.isfile(path + ".zip"):
+            path = path + ".zip"
+        if path.endswith(".pt"):
+            model = cls(env, **kw)
+            model.load_state_dict(torch.load(path, weights_only=False))
+            return model
+        from . import sb3_zip
+        z = sb3_zip.import_zip(path)
+        for k in ("n_steps", "batch_size", "n_epochs", "gamma", "gae_lambda", "learning_rate", "clip_range", "ent_coef",
+                  "vf_coef", "max_grad_norm"):
+            if k in z["hyper"] and k not in kw and isinstance(z["hyper"][k], (int, float)):
+                kw[k] = z["hyper"][k]
         model = cls(env, **kw)
+        sd = {"params": z["params"], "adam": z["adam"] if z["adam"] is not None else torch.zeros(2 * POLICY_PARAMS),
+              "adam_step": z["adam_step"], "num_timesteps": int(z["hyper"].get("num_timesteps", 0) or 0),
+              "n_updates": int(z["hyper"].get("_n_updates", 0) or 0)}
+        if z["extra"]:
+            sd.update(z["extra"])
         model.load_state_dict(sd)
         return model

@@ -1,0 +1,131 @@
+"""Host-side pieces of the training driver (reference train.py / helper.py / traj_tb.py) -- CPU only."""
+import io
+import json
+import os
+import zipfile
+
+import numpy as np
+import torch
+
+from drone_rl_b200 import sb3_zip
+from drone_rl_b200.ppo import POLICY_PARAMS, SB3_NAMES, init_policy_params, unpack_params
+from drone_rl_b200.train import RunLogger, TrajectoryCallback, make_run_dir
+
+
+def test_make_run_dir_numbers_like_the_reference(tmp_path):
+    """helper.py:6-21: drone_runs_1, drone_runs_2 exist -> drone_runs_3; gaps are not reused; other names ignored."""
+    root = tmp_path / "tensorboard"
+    assert make_run_dir(str(root)).endswith("drone_runs_1")
+    assert make_run_dir(str(root)).endswith("drone_runs_2")
+    os.makedirs(root / "drone_runs_7")
+    os.makedirs(root / "drone_runs_x")
+    os.makedirs(root / "other_3")
+    assert make_run_dir(str(root)).endswith("drone_runs_8")
+    assert make_run_dir(str(root), prefix="other_").endswith("other_4")
+
+
+def test_run_logger_writes_sb3_keys(tmp_path, capsys):
+    lg = RunLogger(str(tmp_path), stdout=True)
+    lg.dump({"rollout/ep_rew_mean": -1.5, "rollout/ep_len_mean": 31.0, "train/value_loss": 0.25, "time/iterations": 1}, 2048)
+    lg.dump({"rollout/ep_rew_mean": -1.2, "rollout/ep_len_mean": 33.0, "train/value_loss": 0.2, "time/iterations": 2}, 4096)
+    lg.close()
+    rows = open(tmp_path / "progress.csv").read().strip().splitlines()
+    assert rows[0] == "step,rollout/ep_rew_mean,rollout/ep_len_mean,train/value_loss,time/iterations" and len(rows) == 3
+    js = [json.loads(l) for l in open(tmp_path / "progress.jsonl")]
+    assert js[1]["step"] == 4096 and js[1]["rollout/ep_rew_mean"] == -1.2
+    out = capsys.readouterr().out
+    assert "| rollout/" in out and "ep_rew_mean" in out and "| train/" in out
+
+
+class _FakeModel:
+    def __init__(self, pos, done):
+        class B:
+            pass
+        self.buf = B()
+        obs = torch.zeros(pos.shape[0], 2, 15)
+        obs[:, 0, 0:3] = torch.from_numpy(pos)
+        self.buf.obs, self.buf.done = obs, torch.from_numpy(done.astype(np.uint8))[:, None].repeat(1, 2)
+        self.num_timesteps = 1234
+
+
+def test_trajectory_callback_segments_episodes(tmp_path):
+    """traj_tb.py:31-73: every record_interval-th episode is buffered, every block_size episodes a block is written."""
+    K = 60
+    pos = np.arange(K * 3, dtype=np.float32).reshape(K, 3)
+    done = np.zeros(K, bool)
+    done[[9, 19, 29, 39, 49, 59]] = True                     # six episodes of ten steps
+    cb = TrajectoryCallback(str(tmp_path), record_interval=2, block_size=4)
+    assert cb(_FakeModel(pos[:25], done[:25])) is True       # rollouts may cut an episode in two
+    assert cb(_FakeModel(pos[25:], done[25:])) is True
+    assert cb.episode_count == 6 and cb.blocks_written == 1
+    z = np.load(tmp_path / "trajectory_block1.npz")
+    assert set(z.files) == {"step", "ep_2", "ep_4"}
+    assert np.array_equal(z["ep_2"], pos[10:20]) and np.array_equal(z["ep_4"], pos[30:40])
+    assert len(cb.buffered) == 1 and np.array_equal(cb.buffered[0], pos[50:60])   # episode 6, next block
+    assert os.path.isfile(tmp_path / "trajectory_block1.png")
+
+
+def _sb3_like_archive(path, params, m, v, step):
+    """An archive laid out the way stable-baselines3 writes it: state_dict in ``parameters()`` order, Adam state
+    keyed by parameter index, ``data`` json with a non-json-able member stored as a dict."""
+    named = {SB3_NAMES[k]: t.clone() for k, t in unpack_params(params).items()}
+    nm, nv = ({SB3_NAMES[k]: t.clone() for k, t in unpack_params(x).items()} for x in (m, v))
+    order = sb3_zip.SB3_PARAM_ORDER
+    policy = {k: named[k] for k in order}
+    opt = {"state": {i: {"step": torch.tensor(float(step)), "exp_avg": nm[k], "exp_avg_sq": nv[k]} for i, k in enumerate(order)},
+           "param_groups": [{"lr": 3e-4, "params": list(range(len(order)))}]}
+
+    def pth(o):
+        b = io.BytesIO(); torch.save(o, b); return b.getvalue()
+    with zipfile.ZipFile(path, "w") as z:
+        z.writestr("data", json.dumps({"n_steps": 2048, "batch_size": 64, "gamma": 0.99, "policy_class": {":type:": "x", ":serialized:": "abc"}}))
+        z.writestr("policy.pth", pth(policy))
+        z.writestr("policy.optimizer.pth", pth(opt))
+        z.writestr("pytorch_variables.pth", pth({}))
+        z.writestr("_stable_baselines3_version", "2.3.0")
+
+
+def test_sb3_zip_import_and_export_round_trip(tmp_path):
+    g = torch.Generator().manual_seed(3)
+    params = init_policy_params(5) + 0.01 * torch.randn(POLICY_PARAMS, generator=g)
+    m, v = torch.randn(POLICY_PARAMS, generator=g), torch.rand(POLICY_PARAMS, generator=g)
+    p = str(tmp_path / "dd.zip")
+    _sb3_like_archive(p, params, m, v, 320)
+    z = sb3_zip.import_zip(p)
+    assert torch.equal(z["params"], params) and z["adam_step"] == 320
+    assert torch.equal(z["adam"], torch.cat([m, v]))
+    assert z["hyper"] == {"n_steps": 2048, "batch_size": 64, "gamma": 0.99} and z["extra"] is None
+    # ours -> archive -> back, including the env / curriculum extras
+    q = str(tmp_path / "ours.zip")
+    extra = {"num_timesteps": 4096, "n_updates": 640, "env_state": {"ep_num": np.arange(4)}, "env_global_step": 77}
+    sb3_zip.export_zip(q, params, torch.cat([m, v]), 640, {"n_steps": 128, "learning_rate": 1e-3}, extra)
+    names = set(zipfile.ZipFile(q).namelist())
+    assert {"data", "policy.pth", "policy.optimizer.pth", "pytorch_variables.pth", "_stable_baselines3_version"} <= names
+    z2 = sb3_zip.import_zip(q)
+    assert torch.equal(z2["params"], params) and torch.equal(z2["adam"], torch.cat([m, v])) and z2["adam_step"] == 640
+    assert z2["hyper"]["n_steps"] == 128 and z2["extra"]["env_global_step"] == 77
+    # the policy member is what SB3's set_parameters() feeds to policy.load_state_dict: SB3 names, parameters() order
+    sd = torch.load(io.BytesIO(zipfile.ZipFile(q).read("policy.pth")), weights_only=False)
+    assert list(sd) == sb3_zip.SB3_PARAM_ORDER
+    assert sd["action_net.weight"].shape == (4, 64) and sd["mlp_extractor.value_net.0.weight"].shape == (64, 15)
+    # a torch module with SB3's structure accepts it
+    class Extractor(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.policy_net = torch.nn.Sequential(torch.nn.Linear(15, 64), torch.nn.Tanh(), torch.nn.Linear(64, 64), torch.nn.Tanh())
+            self.value_net = torch.nn.Sequential(torch.nn.Linear(15, 64), torch.nn.Tanh(), torch.nn.Linear(64, 64), torch.nn.Tanh())
+    class Policy(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.mlp_extractor = Extractor()
+            self.action_net = torch.nn.Linear(64, 4)
+            self.log_std = torch.nn.Parameter(torch.zeros(4))
+            self.value_net = torch.nn.Linear(64, 1)
+    pol = Policy()
+    pol.load_state_dict(sd, strict=True)
+    # forward of that module == the oracle's forward of the flat vector
+    from oracle import ppo_oracle as po
+    x = torch.randn(7, 15, generator=g)
+    mean, value, _ = po.forward(params, x)
+    assert torch.allclose(pol.action_net(pol.mlp_extractor.policy_net(x)), mean, atol=1e-6)
+    assert torch.allclose(pol.value_net(pol.mlp_extractor.value_net(x)).squeeze(-1), value, atol=1e-6)
