@@ -163,6 +163,35 @@ extern "C" int dronecu_ppo_destroy(dronecu_ppo* p) {
 
 extern "C" int64_t dronecu_ppo_num_updates(const dronecu_ppo* p) { return p ? p->step : 0; }
 
+// host copy of Philox4x32-10 (philox.cuh is device code)
+static void philox_host(uint32_t c[4], uint32_t k0, uint32_t k1) {
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c[0], p1 = (uint64_t)0xCD9E8D57u * c[2];
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1;
+    c[0] = n0; c[1] = (uint32_t)p1; c[2] = n2; c[3] = (uint32_t)p0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+
+extern "C" int dronecu_minibatch_permutation(int device, int64_t n, uint64_t seed, uint64_t epoch, int32_t* d_out,
+                                             void* stream) {
+  if (!d_out || n <= 0 || n > ((int64_t)1 << 31) - 1) return fail(DRONECU_ERR_INVALID, "dronecu_minibatch_permutation: bad argument");
+  DeviceGuard guard(device);
+  PermKey K;
+  int bits = 1;
+  while (((int64_t)1 << bits) < n) ++bits;
+  K.mask = (bits >= 32) ? 0xFFFFFFFFu : ((1u << bits) - 1u);
+  K.shift = (uint32_t)((bits + 1) / 2);
+  for (int r = 0; r < 4; r += 2) {        // two Philox calls: 4 multipliers, 4 addends
+    uint32_t c[4] = {(uint32_t)epoch, (uint32_t)(epoch >> 32), (uint32_t)r, 0x5045524Du /* "PERM" */};
+    philox_host(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    K.mul[r] = c[0] | 1u; K.mul[r + 1] = c[1] | 1u; K.add[r] = c[2]; K.add[r + 1] = c[3];
+  }
+  perm_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_out, (uint32_t)n, K);
+  CUDA_TRY(cudaGetLastError());
+  return DRONECU_OK;
+}
+
 extern "C" int dronecu_ppo_adv_stats(dronecu_ppo* p, const float* d_adv, const int32_t* d_index, int64_t first,
                                      int64_t m, double* d_out, void* stream) {
   if (!p || !d_adv || !d_out || m <= 0) return fail(DRONECU_ERR_INVALID, "dronecu_ppo_adv_stats: bad argument");

@@ -456,4 +456,32 @@ __global__ void __launch_bounds__(1024) ppo_apply_kernel(const AdamArgs A) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Minibatch order: SB3 draws np.random.permutation(B) once per epoch (PPO.train -> RolloutBuffer.get).  Here the
+// permutation is a keyed bijection evaluated per element -- no sort, no scratch: on k = ceil(log2 B) bits,
+// four rounds of  x = ((x ^ (x >> s)) * odd + add) mod 2^k  (each step is a bijection on k-bit integers), with
+// the multipliers / addends taken from Philox4x32-10(key = seed, counter = (epoch, round)), and cycle-walking
+// (re-apply until the value is < B; < 2 applications on average).  oracle/philox.py: minibatch_permutation.
+// ---------------------------------------------------------------------------------------------
+struct PermKey {
+  uint32_t mul[4], add[4];
+  uint32_t mask, shift;
+};
+
+__host__ __device__ inline uint32_t perm_apply(uint32_t x, const PermKey& K, uint32_t n) {
+  do {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      x ^= x >> K.shift;
+      x = (x * K.mul[r] + K.add[r]) & K.mask;
+    }
+  } while (x >= n);
+  return x;
+}
+
+__global__ void perm_kernel(int32_t* __restrict__ out, uint32_t n, const __grid_constant__ PermKey K) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (int32_t)perm_apply(i, K, n);
+}
+
 }  // namespace dronecu

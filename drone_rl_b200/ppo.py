@@ -132,6 +132,7 @@ class PPO:
         self._info = torch.zeros(9, dtype=torch.float32, device=self.device)
         self._gen = torch.Generator(device=self.device).manual_seed(seed + 1)
         self.num_timesteps, self.n_updates = 0, 0
+        self._perm, self._epochs_done = None, 0
         self.logger_values: dict = {}
         self.launches = 0
         self.batch.reset()          # SB3 _setup_learn: env.reset()  (ep_num 1 -> 2)
@@ -189,8 +190,15 @@ class PPO:
     def train(self):
         """SB3 PPO.train(): n_epochs passes over the buffer in random minibatches of batch_size."""
         B = self.n_steps * self.n_envs
+        if self._perm is None or self._perm.numel() != B:
+            self._perm = torch.empty(B, dtype=torch.int32, device=self.device)
+        perm = self._perm
         for _ in range(self.n_epochs):
-            perm = torch.randperm(B, device=self.device, generator=self._gen, dtype=torch.int64).to(torch.int32)
+            # SB3: np.random.permutation(B) per epoch; here a keyed bijection evaluated on the device (no sort)
+            _lib.check(self.lib.dronecu_minibatch_permutation(self.device.index, B, self.seed + 1, self._epochs_done,
+                                                              _ptr(perm), _stream_ptr(self.device)), "dronecu_minibatch_permutation")
+            self._epochs_done += 1
+            self.launches += 1
             for start in range(0, B, self.batch_size):
                 m = min(self.batch_size, B - start)
                 self._minibatch(perm[start:start + m], 0, m)
@@ -261,7 +269,7 @@ class PPO:
         _lib.check(self.lib.dronecu_ppo_get_state(self._h, _ptr(mom), C.byref(step), _stream_ptr(self.device)))
         torch.cuda.synchronize(self.device)
         return {"params": self.params.cpu(), "adam": mom.cpu(), "adam_step": step.value,
-                "num_timesteps": self.num_timesteps, "n_updates": self.n_updates,
+                "num_timesteps": self.num_timesteps, "n_updates": self.n_updates, "epochs_done": self._epochs_done,
                 "env_state": self.batch.get_state(), "env_global_step": self.batch.global_step,
                 "sb3_policy": {SB3_NAMES[k]: v.clone() for k, v in unpack_params(self.params.cpu()).items()}}
 
@@ -271,6 +279,7 @@ class PPO:
                                                   _stream_ptr(self.device)))
         torch.cuda.synchronize(self.device)
         self.num_timesteps, self.n_updates = sd["num_timesteps"], sd["n_updates"]
+        self._epochs_done = int(sd.get("epochs_done", 0))
         if load_env and "env_state" in sd and sd["env_state"]["pos"].shape[0] == self.n_envs:
             self.batch.set_state(**sd["env_state"])
             self.batch.global_step = sd.get("env_global_step", self.batch.global_step)
@@ -288,7 +297,7 @@ class PPO:
                  "clip_range": float(self.cfg.clip_range), "ent_coef": float(self.cfg.ent_coef),
                  "vf_coef": float(self.cfg.vf_coef), "max_grad_norm": float(self.cfg.max_grad_norm),
                  "n_envs": self.n_envs, "num_timesteps": self.num_timesteps, "_n_updates": self.n_updates, "seed": self.seed}
-        extra = {k: sd[k] for k in ("num_timesteps", "n_updates", "env_state", "env_global_step")}
+        extra = {k: sd[k] for k in ("num_timesteps", "n_updates", "epochs_done", "env_state", "env_global_step")}
         sb3_zip.export_zip(path if path.endswith(".zip") else path + ".zip", sd["params"], sd["adam"], sd["adam_step"],
                            hyper, extra)
 

@@ -241,6 +241,12 @@ void dronecu_ppo_config_default(dronecu_ppo_config* cfg); /* the SB3 defaults li
 int dronecu_ppo_create(const dronecu_ppo_config* cfg, int device, dronecu_ppo** out);
 int dronecu_ppo_destroy(dronecu_ppo* ppo);
 
+/* Minibatch order of one epoch: d_out[0..n) = a pseudo-random permutation of 0..n-1 keyed by (seed, epoch).
+ * Replaces SB3's np.random.permutation(buffer_size) (RolloutBuffer.get, called from PPO.train; call site
+ * reference train.py:63) with a keyed bijection evaluated per element on the device -- no sort.  The exact
+ * function is restated in oracle/philox.py (minibatch_permutation); n < 2^31. */
+int dronecu_minibatch_permutation(int device, int64_t n, uint64_t seed, uint64_t epoch, int32_t* d_out, void* stream);
+
 /* sum, sum of squares and count of the advantages of a minibatch, ACCUMULATED into d_out[3] (float64;
  * zero it first).  Minibatch = rows d_index[0..m) of the flat buffers, or rows first..first+m when
  * d_index is NULL.  (Data-parallel training all-reduces d_out before forming mean / std.) */

@@ -104,3 +104,31 @@ def noise_normals(seed: int, env_ids, t):
     a0 = 2.0 * np.pi * u[1]
     a1 = 2.0 * np.pi * u[3]
     return np.stack([r0 * np.cos(a0), r0 * np.sin(a0), r1 * np.cos(a1), r1 * np.sin(a1)], axis=1)
+
+
+def minibatch_permutation(n: int, seed: int, epoch: int) -> np.ndarray:
+    """The keyed permutation of 0..n-1 behind ``dronecu_minibatch_permutation`` (csrc/ppo_update.cuh
+    ``perm_apply``): on k = ceil(log2 n) bits, four rounds of x = ((x ^ (x >> s)) * odd + add) mod 2^k with
+    s = (k + 1) // 2 and the constants from Philox4x32-10(key = seed, counter = (epoch lo, epoch hi, r, "PERM")),
+    cycle-walked until the value is < n.  Stands in for SB3's ``np.random.permutation`` (PARITY UNPINNED: any
+    uniform-looking order satisfies SB3's contract)."""
+    bits = 1
+    while (1 << bits) < n:
+        bits += 1
+    mask = (1 << bits) - 1
+    shift = (bits + 1) // 2
+    mul, add = [0] * 4, [0] * 4
+    for r in (0, 2):
+        c = philox4x32_10(epoch & 0xFFFFFFFF, (epoch >> 32) & 0xFFFFFFFF, r, 0x5045524D,
+                          seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+        mul[r], mul[r + 1], add[r], add[r + 1] = int(c[0]) | 1, int(c[1]) | 1, int(c[2]), int(c[3])
+    x = np.arange(n, dtype=np.uint64)
+    todo = np.ones(n, dtype=bool)
+    while todo.any():
+        y = x[todo]
+        for r in range(4):
+            y ^= y >> np.uint64(shift)
+            y = (y * np.uint64(mul[r]) + np.uint64(add[r])) & np.uint64(mask)
+        x[todo] = y
+        todo[todo] = y >= n
+    return x.astype(np.int64)

@@ -296,3 +296,24 @@ def test_learn_improves_and_checkpoints(drl, tmp_path):
     assert act.shape == (4,) and (act >= 0).all() and (act <= 7.3575 + 1e-6).all()
     for m in (model, m2, m3):
         m.close()
+
+
+@pytest.mark.parametrize("n", [1, 2, 63, 64, 4097, 65536 * 32, 3_000_001])
+def test_minibatch_permutation_matches_oracle(drl, n):
+    """The per-epoch minibatch order (stand-in for SB3's np.random.permutation): bit-exact against the numpy
+    restatement, a true permutation at every size (power of two, ragged, one element), different per epoch."""
+    import ctypes as C
+    from drone_rl_b200 import _lib
+    from oracle import philox
+    lib = _lib.load()
+    out = torch.empty(n, dtype=torch.int32, device="cuda")
+    seen = []
+    for epoch in (0, 1, 2 ** 33 + 5):
+        _lib.check(lib.dronecu_minibatch_permutation(0, n, 12345, epoch, C.c_void_p(out.data_ptr()), None))
+        torch.cuda.synchronize()
+        got = out.cpu().numpy().astype(np.int64)
+        assert np.array_equal(got, philox.minibatch_permutation(n, 12345, epoch))
+        assert np.array_equal(np.sort(got), np.arange(n))
+        seen.append(got)
+    if n > 64:
+        assert (seen[0] == seen[1]).mean() < 0.01 and abs(np.corrcoef(np.arange(n), seen[0])[0, 1]) < 0.05
