@@ -212,6 +212,7 @@ static int ppo_grad_impl(dronecu_ppo* p, const float* d_params, const float* d_o
   if (!p || !d_params || !d_obs || !d_actions || !d_old_logp || !d_adv || !d_returns || !d_grad || m <= 0)
     return fail(DRONECU_ERR_INVALID, "dronecu_ppo_grad: bad argument");
   if (reinterpret_cast<uintptr_t>(d_actions) & 15) return fail(DRONECU_ERR_INVALID, "d_actions must be 16-byte aligned");
+  if (first < 0 || first + m > ((int64_t)1 << 31) - 1) return fail(DRONECU_ERR_INVALID, "dronecu_ppo_grad: row numbers must fit in 31 bits");
   DeviceGuard guard(p->device);
   UpdArgs a;
   a.theta = d_params; a.obs = d_obs; a.actions = reinterpret_cast<const float4*>(d_actions); a.old_logp = d_old_logp;
