@@ -51,6 +51,7 @@
 namespace dronecu {
 namespace tcu {
 
+using tc::elect_one;
 using tc::fence_after;
 using tc::fence_before;
 using tc::mbar_init;
@@ -178,12 +179,6 @@ __device__ __forceinline__ float* xa_elem(unsigned char* xa, int n, int s) {
 // element (sample m, feature k) of the X tile
 __device__ __forceinline__ float* xs_elem(unsigned char* xs, int m, int k) {
   return reinterpret_cast<float*>(xs + (m >> 3) * kXsSbo + (k >> 2) * kXsLbo + ((m & 7) << 4) + ((k & 3) << 2));
-}
-
-__device__ __forceinline__ uint32_t elect_one() {       // one lane of the (converged) warp; tells ptxas the region is single-threaded
-  uint32_t pred = 0;
-  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
-  return pred;
 }
 
 // a compute thread's staged operands (generic-proxy smem writes, tcgen05.st) are handed to the issuer

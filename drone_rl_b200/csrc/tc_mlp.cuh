@@ -106,6 +106,12 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
   } while (!done);
 }
 
+__device__ __forceinline__ uint32_t elect_one() {       // one lane of the (converged) warp; tells ptxas the region is single-threaded
+  uint32_t pred = 0;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+  return pred;
+}
+
 __device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
@@ -193,7 +199,7 @@ __device__ __forceinline__ void tower(Smem& S, const int t, const float (&xv)[16
   wait_st();
   fence_before();
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (threadIdx.x < 32 && elect_one()) {       // elect.sync: ptxas keeps the descriptors uniform (no per-MMA waterfall loop)
     fence_after();
     constexpr uint32_t idesc1 = make_idesc(kTile, kN1);
 #pragma unroll
@@ -222,7 +228,7 @@ __device__ __forceinline__ void tower(Smem& S, const int t, const float (&xv)[16
   wait_st();
   fence_before();
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (threadIdx.x < 32 && elect_one()) {
     fence_after();
     constexpr uint32_t idesc2 = make_idesc(kTile, kN2);
 #pragma unroll
