@@ -419,12 +419,32 @@ def run_ppo(args):
     barrier()
     l0 = env.launch_count + model.launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    model.grad_events = [] if wl == "c5" else None
+    roll_events = []
     with ClockSampler(local) as clocks:
         ev0.record()
         for _ in range(args.steps):
+            if wl == "c3":
+                e = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                e[0].record()
             one_step()
+            if wl == "c3":
+                e[1].record()
+                roll_events.append(e)
         ev1.record()
         barrier()
+    # the dominant kernel of the workload, timed live by CUDA events on the launching stream
+    if wl == "c5":
+        ms = [a.elapsed_time(b) for a, b, _ in model.grad_events]
+        units = float(np.mean([m for _, _, m in model.grad_events]))
+        kflop, kname = 3 * 20864.0, ("ppo_grad_tc_kernel" if (args.update_precision or args.precision) == "tf32" else "ppo_grad_kernel") + " (+ its fixed-order reduce)"
+        model.grad_events = None
+    else:
+        ms = [a.elapsed_time(b) for a, b in roll_events]
+        units = float(n * K)
+        kflop, kname = 20864.0, ("policy_rollout_tc_kernel" if args.precision == "tf32" else "policy_rollout_kernel") + " (+ gae_kernel)"
+    k_ms = float(np.mean(ms))
+    k_tflops = units * kflop / (k_ms * 1e-3) / 1e12
     launches = env.launch_count + model.launches - l0
     t = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
     if world > 1:
@@ -471,8 +491,9 @@ def run_ppo(args):
                            "minibatches_per_epoch": args.ppo_minibatches, "policy": "MlpPolicy 15-64-64-{4,1} tanh, random init", "rollout_precision": args.precision,
                            "update_precision": args.update_precision or args.precision,
                            "l2": "rollout buffers %.1f GB per iteration, larger than L2" % (n * K * 93 / 1e9)},
-                "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                             "traffic": None, "note": ("tcgen05 kind::tf32 MMAs (tf32 dense peak = half the bf16 peak used as the "
+                "roofline": {"bound": "tensor", "achieved": k_tflops, "peak": peak, "unit": "TFLOP/s", "frac": k_tflops / peak,
+                             "traffic": None, "kernel": kname, "avg_launch_ms": k_ms, "units_per_launch": units,
+                             "algorithmic_flop_per_unit": kflop, "whole_step_tflops": achieved, "note": ("tcgen05 kind::tf32 MMAs (tf32 dense peak = half the bf16 peak used as the "
                              "denominator)" if tensor else "fp32 CUDA-core parity path (nominal 74.4 TFLOP/s FMA peak: frac_of_fp32 = "
                              "%.3f); the denominator is the measured bf16 tensor peak" % (achieved / 74.4)),
                              "flop_per_env_step": flop_per_step},

@@ -133,6 +133,7 @@ class PPO:
         self._gen = torch.Generator(device=self.device).manual_seed(seed + 1)
         self.num_timesteps, self.n_updates = 0, 0
         self._perm, self._epochs_done = None, 0
+        self.grad_events = None                   # set to [] to collect (start, end, samples) events per gradient launch
         self.logger_values: dict = {}
         self.launches = 0
         self.batch.reset()          # SB3 _setup_learn: env.reset()  (ep_num 1 -> 2)
@@ -177,9 +178,15 @@ class PPO:
             stats_ptr = _ptr(self._adv_stats)
             self.launches += 2
         grad_fn = self.lib.dronecu_ppo_grad_tc if self.update_precision == "tf32" else self.lib.dronecu_ppo_grad
+        if self.grad_events is not None:          # bench.py: CUDA events around the gradient launches
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), m)
+            ev[0].record()
         _lib.check(grad_fn(self._h, _ptr(self.params), _ptr(b.obs), _ptr(b.actions), _ptr(b.logp),
                            _ptr(b.adv), _ptr(b.ret), _ptr(index), first, m, 0.0, 1.0, stats_ptr,
                            _ptr(self._grad), st), "dronecu_ppo_grad")
+        if self.grad_events is not None:
+            ev[1].record()
+            self.grad_events.append(ev)
         if self.world > 1:
             torch.distributed.all_reduce(self._grad)      # NCCL: 42.8 KB, the only collective of the data path
         _lib.check(self.lib.dronecu_ppo_apply(self._h, _ptr(self.params), _ptr(self._grad),
