@@ -444,3 +444,33 @@ def test_chunked_host_step_equals_device_step(drl):
     assert venv.batch.global_step == ref.global_step == 3
     assert venv.episode_stats()["env_steps"] == 3 * n
     venv.close(); ref.close()
+
+
+@pytest.mark.parametrize("scale", [1.0, 50.0, 3e3, 1.0e5, 1.056e5, 1.0e7])
+def test_euler_angle_range_of_sincos(drl, scale):
+    """The kernel's own sin/cos of the three Euler angles (one range check, Cody-Waite by pi/2 below 105615 rad,
+    libm above) against the float64 oracle, teacher-forced, for angles from +-1 rad up to +-1e7 rad -- the reference
+    never wraps its angles (drone.py:131), so every magnitude a long episode can reach must stay within 1e-5
+    relative.  Mixed rows (one angle above the fast-path limit, two below) exercise the shared range check."""
+    rng = np.random.default_rng(int(scale) % 9973)
+    n = 8192
+    pos = rng.uniform(-5, 5, (n, 3)).astype(np.float32); pos[:, 2] = np.abs(pos[:, 2]) + 1
+    vel = rng.uniform(-3, 3, (n, 3)).astype(np.float32)
+    euler = (rng.uniform(-1, 1, (n, 3)) * scale).astype(np.float32)
+    euler[::7, rng.integers(0, 3)] *= 0.01                    # mixed magnitudes within a row
+    # keep pitch away from the tan / sec singularity: the amplification there is covered by the golden cases
+    c = np.cos(euler[:, 1].astype(np.float64))
+    euler[np.abs(c) < 0.05, 1] += np.float32(0.3)
+    omega = rng.uniform(-2, 2, (n, 3)).astype(np.float32)
+    target = rng.uniform(-1, 1, (n, 3)).astype(np.float32)
+    action = rng.uniform(0, 7.3575, (n, 4)).astype(np.float32)
+    res, orc = _tf_step(drl, do.SINGLE, pos, vel, euler, omega, target, action, np.zeros(n, np.int32), auto_reset=False)
+    st, o = res["state"], orc["env"]
+    got = np.concatenate([st["pos"], st["vel"], st["euler"], st["omega"]], 1)
+    ref = np.concatenate([o.pos, o.vel, o.euler, o.omega], 1)
+    cosp = np.cos(euler[:, 1].astype(np.float64))
+    amp = np.ones((n, 12))
+    amp[:, 6] = amp[:, 8] = np.maximum(1.0, 1.0 / cosp ** 2)      # roll / yaw rates carry tan / sec of the pitch
+    worst = _assert_close(got, ref, amp, f"state at |angle| <= {scale:g}")
+    _assert_close(res["reward"], orc["reward"], 1.0, "reward")
+    print(f"scale {scale:g}: worst err/bound = {worst:.3f}")
