@@ -199,3 +199,22 @@ def test_tc_update_trains_like_fp32(drl):
         ps.append(m.params.clone())
         m.close()
     assert (ps[0] - ps[1]).abs().max().item() < 2e-3
+
+
+def test_tc_gradient_is_race_free_under_repetition(drl):
+    """40 back-to-back launches of the tensor-core gradient over the same ragged minibatch (several tiles per
+    warpgroup, a partial last tile, an idle warpgroup tail) must be bit-identical: the kernel's hand-overs
+    (mbarriers, tcgen05 fences, async-proxy fences) leave no window for a stale operand."""
+    from tests.test_gpu_ppo import _rand_params
+    from drone_rl_b200.ppo import PPO
+    m = 128 * 2 * 74 * 3 + 128 * 5 + 77
+    n, K = 2048, (m + 2047) // 2048 + 1
+    model = PPO(n, n_steps=K, ent_coef=0.01)
+    model.params.copy_(_rand_params(11, 0.5).float().cuda())
+    _separated_buffers(model, 6)
+    idx = torch.randperm(n * K, generator=torch.Generator().manual_seed(2))[:m].to(torch.int32).cuda()
+    first = _grad(model, idx, m, tc=True)
+    assert np.isfinite(first).all() and np.abs(first).max() > 0
+    for _ in range(40):
+        assert np.array_equal(_grad(model, idx, m, tc=True), first)
+    model.close()
