@@ -437,7 +437,8 @@ def run_ppo(args):
     if wl == "c5":
         ms = [a.elapsed_time(b) for a, b, _ in model.grad_events]
         units = float(np.mean([m for _, _, m in model.grad_events]))
-        kflop, kname = 3 * 20864.0, ("ppo_grad_tc_kernel" if (args.update_precision or args.precision) == "tf32" else "ppo_grad_kernel") + " (+ its fixed-order reduce)"
+        up = args.update_precision or args.precision
+        kflop, kname = 3 * 20864.0, {"tf32": "ppo_grad_tc_kernel", "bf16": "ppo_grad_bf16_kernel", "fp32": "ppo_grad_kernel"}[up] + " (+ its fixed-order reduce)"
         model.grad_events = None
     else:
         ms = [a.elapsed_time(b) for a, b in roll_events]
@@ -455,7 +456,7 @@ def run_ppo(args):
     pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.isfile(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
     peak = float(pk.get("bf16_tflops_sustained", 1400.0))
     achieved = value / world * flop_per_step / 1e12
-    tensor = (args.precision == "tf32") and (wl == "c3" or (args.update_precision or args.precision) == "tf32")
+    tensor = (args.precision == "tf32") and (wl == "c3" or (args.update_precision or args.precision) in ("tf32", "bf16"))
 
     # ---- e2e: the public API (PPO.collect_rollouts / PPO.learn), wall clock, every iteration reads its
     # result (episode statistics + train/* scalars) back to the host.  The simulator lives on the GPU, so an
@@ -525,7 +526,7 @@ def main():
     ap.add_argument("--ppo-epochs", type=int, default=10)
     ap.add_argument("--ppo-minibatches", type=int, default=4)
     ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32"], help="policy MLP in the rollout: CUDA cores or tcgen05")
-    ap.add_argument("--update-precision", default=None, choices=["fp32", "tf32"], help="PPO minibatch gradient: CUDA cores or tcgen05 (default: same as --precision)")
+    ap.add_argument("--update-precision", default=None, choices=["fp32", "tf32", "bf16"], help="PPO minibatch gradient: CUDA cores or tcgen05 (default: same as --precision)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

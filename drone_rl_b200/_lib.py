@@ -113,6 +113,7 @@ _SIGNATURES = {
     "dronecu_ppo_adv_stats": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, _P, _P]),
     "dronecu_ppo_grad": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int64, C.c_float, C.c_float, _P, _P, _P]),
     "dronecu_ppo_grad_tc": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int64, C.c_float, C.c_float, _P, _P, _P]),
+    "dronecu_ppo_grad_bf16": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int64, C.c_float, C.c_float, _P, _P, _P]),
     "dronecu_ppo_debug_buffer": (C.c_int, [_P, _P]),
     "dronecu_ppo_apply": (C.c_int, [_P, _P, _P, C.c_double, _P, _P]),
     "dronecu_ppo_num_updates": (C.c_int64, [_P]),

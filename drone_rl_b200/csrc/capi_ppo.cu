@@ -13,6 +13,7 @@
 #include "ppo_update.cuh"
 #include "ppo_rollout_tc.cuh"
 #include "ppo_update_tc.cuh"
+#include "ppo_update_tc3.cuh"
 
 using namespace dronecu;
 
@@ -147,6 +148,7 @@ extern "C" int dronecu_ppo_create(const dronecu_ppo_config* cfg, int device, dro
   CUDA_TRY(cudaMemset(p->moments, 0, sizeof(float) * 2 * kParams));
   CUDA_TRY(cudaFuncSetAttribute(ppo_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UpdSmem)));
   CUDA_TRY(cudaFuncSetAttribute(ppo_grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcUpdSmem));
+  CUDA_TRY(cudaFuncSetAttribute(ppo_grad_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTc3Smem));
   *out = p;
   return DRONECU_OK;
 }
@@ -208,7 +210,8 @@ extern "C" int dronecu_ppo_adv_stats(dronecu_ppo* p, const float* d_adv, const i
 static int ppo_grad_impl(dronecu_ppo* p, const float* d_params, const float* d_obs, const float* d_actions,
                          const float* d_old_logp, const float* d_adv, const float* d_returns,
                          const int32_t* d_index, int64_t first, int64_t m, float adv_mean, float adv_inv_std,
-                         const double* d_adv_stats, float* d_grad, void* stream, bool tensor_cores) {
+                         const double* d_adv_stats, float* d_grad, void* stream, int mode) {
+  const bool tensor_cores = mode != 0;
   if (!p || !d_params || !d_obs || !d_actions || !d_old_logp || !d_adv || !d_returns || !d_grad || m <= 0)
     return fail(DRONECU_ERR_INVALID, "dronecu_ppo_grad: bad argument");
   if (reinterpret_cast<uintptr_t>(d_actions) & 15) return fail(DRONECU_ERR_INVALID, "d_actions must be 16-byte aligned");
@@ -222,7 +225,13 @@ static int ppo_grad_impl(dronecu_ppo* p, const float* d_params, const float* d_o
   a.partials = p->partials; a.dbg = tensor_cores ? p->dbg : nullptr;
   const int64_t tiles = (m + kUpdBlock - 1) / kUpdBlock;
   cudaStream_t st = (cudaStream_t)stream;
-  if (tensor_cores) {
+  if (mode == 2) {
+    // grid (x, 2): blockIdx.y = tower; one CTA per SM, three 128-sample tiles in flight per CTA, one partial vector per CTA
+    const unsigned gx = (unsigned)std::max<int64_t>(1, std::min<int64_t>((tiles + tcb::kWG3 - 1) / tcb::kWG3, p->n_sm / 2));
+    ppo_grad_bf16_kernel<<<dim3(gx, 2), tcb::kThreads3, kTc3Smem, st>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    ppo_reduce_tc_kernel<<<(kGradLen + 255) / 256, 256, 0, st>>>(p->partials, (int)gx, d_grad);
+  } else if (tensor_cores) {
     // grid (x, 2): blockIdx.y = tower; one CTA per SM, two 128-sample tiles in flight per CTA
     const unsigned gx = (unsigned)std::max<int64_t>(1, std::min<int64_t>((tiles + tcu::kWG - 1) / tcu::kWG, p->n_sm / 2));
     ppo_grad_tc_kernel<<<dim3(gx, 2), tcu::kThreads, kTcUpdSmem, st>>>(a);
@@ -244,7 +253,7 @@ extern "C" int dronecu_ppo_grad(dronecu_ppo* p, const float* d_params, const flo
                                 const int32_t* d_index, int64_t first, int64_t m, float adv_mean, float adv_inv_std,
                                 const double* d_adv_stats, float* d_grad, void* stream) {
   return ppo_grad_impl(p, d_params, d_obs, d_actions, d_old_logp, d_adv, d_returns, d_index, first, m, adv_mean,
-                       adv_inv_std, d_adv_stats, d_grad, stream, false);
+                       adv_inv_std, d_adv_stats, d_grad, stream, 0);
 }
 
 extern "C" int dronecu_ppo_grad_tc(dronecu_ppo* p, const float* d_params, const float* d_obs, const float* d_actions,
@@ -252,7 +261,15 @@ extern "C" int dronecu_ppo_grad_tc(dronecu_ppo* p, const float* d_params, const 
                                    const int32_t* d_index, int64_t first, int64_t m, float adv_mean, float adv_inv_std,
                                    const double* d_adv_stats, float* d_grad, void* stream) {
   return ppo_grad_impl(p, d_params, d_obs, d_actions, d_old_logp, d_adv, d_returns, d_index, first, m, adv_mean,
-                       adv_inv_std, d_adv_stats, d_grad, stream, true);
+                       adv_inv_std, d_adv_stats, d_grad, stream, 1);
+}
+
+extern "C" int dronecu_ppo_grad_bf16(dronecu_ppo* p, const float* d_params, const float* d_obs, const float* d_actions,
+                                     const float* d_old_logp, const float* d_adv, const float* d_returns,
+                                     const int32_t* d_index, int64_t first, int64_t m, float adv_mean, float adv_inv_std,
+                                     const double* d_adv_stats, float* d_grad, void* stream) {
+  return ppo_grad_impl(p, d_params, d_obs, d_actions, d_old_logp, d_adv, d_returns, d_index, first, m, adv_mean,
+                       adv_inv_std, d_adv_stats, d_grad, stream, 2);
 }
 
 extern "C" int dronecu_ppo_debug_buffer(dronecu_ppo* p, float* d_dbg) {

@@ -114,8 +114,9 @@ class PPO:
         self.verbose, self.seed = verbose, seed
         if rollout_precision not in ("fp32", "tf32"):
             raise ValueError("rollout_precision must be 'fp32' (CUDA cores, parity path) or 'tf32' (tcgen05 tensor cores)")
-        if update_precision not in ("fp32", "tf32"):
-            raise ValueError("update_precision must be 'fp32' (CUDA cores, parity path) or 'tf32' (tcgen05 tensor cores)")
+        if update_precision not in ("fp32", "tf32", "bf16"):
+            raise ValueError("update_precision must be 'fp32' (CUDA cores, parity path), 'tf32' (tcgen05, all products tf32) or "
+                             "'bf16' (tcgen05, weight-gradient products with bf16 operands, three tiles per SM)")
         self.rollout_precision, self.update_precision = rollout_precision, update_precision
         cfg = PPOConfig()
         self.lib.dronecu_ppo_config_default(C.byref(cfg))
@@ -177,7 +178,8 @@ class PPO:
                 torch.distributed.all_reduce(self._adv_stats)
             stats_ptr = _ptr(self._adv_stats)
             self.launches += 2
-        grad_fn = self.lib.dronecu_ppo_grad_tc if self.update_precision == "tf32" else self.lib.dronecu_ppo_grad
+        grad_fn = {"fp32": self.lib.dronecu_ppo_grad, "tf32": self.lib.dronecu_ppo_grad_tc,
+                   "bf16": self.lib.dronecu_ppo_grad_bf16}[self.update_precision]
         if self.grad_events is not None:          # bench.py: CUDA events around the gradient launches
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), m)
             ev[0].record()

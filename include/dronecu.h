@@ -271,6 +271,15 @@ int dronecu_ppo_grad_tc(dronecu_ppo* ppo, const float* d_params, const float* d_
                         int64_t first, int64_t m, float adv_mean, float adv_inv_std, const double* d_adv_stats,
                         float* d_grad, void* stream);
 
+/* Same contract, three sample tiles in flight per SM: forward and activation-gradient products as above (tf32, A operand
+ * in TMEM), the four weight-gradient products with bf16 operands (kind::f16, fp32 accumulation; dW2 and db2 fused into
+ * one N = 72 product), tanh'(layer 1) stashed as bf16 (csrc/ppo_update_tc3.cuh).  Bit-reproducible (the issuer serves
+ * the warpgroups in a fixed rotation).  Agrees with dronecu_ppo_grad to a few 1e-3 of each block's largest entry. */
+int dronecu_ppo_grad_bf16(dronecu_ppo* ppo, const float* d_params, const float* d_obs, const float* d_actions,
+                          const float* d_old_logp, const float* d_adv, const float* d_returns, const int32_t* d_index,
+                          int64_t first, int64_t m, float adv_mean, float adv_inv_std, const double* d_adv_stats,
+                          float* d_grad, void* stream);
+
 /* Debugging aid for dronecu_ppo_grad_tc: when d_dbg is not NULL the next calls also dump the raw TMEM image
  * of every warpgroup, float32 [2 * grid.x, 128 lanes, 256 columns] (policy-tower CTAs; grid.x = min(ceil(tiles / 2), SMs / 2)) (grid = min(ceil(tiles / 2), SM count)). */
 int dronecu_ppo_debug_buffer(dronecu_ppo* ppo, float* d_dbg);

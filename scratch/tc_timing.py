@@ -5,11 +5,13 @@ import drone_rl_b200 as drl
 from drone_rl_b200 import _lib
 from drone_rl_b200.ppo import PPO
 np.set_printoptions(linewidth=220, suppress=True)
+mode = sys.argv[1] if len(sys.argv) > 1 else "tf32"
+nwg = 3 if mode == "bf16" else 2
 tiles_per_wg = 12
-m = 128 * 2 * 74 * tiles_per_wg
+m = 128 * nwg * 74 * tiles_per_wg
 n = 8192
 K = (m + n - 1) // n + 1
-model = PPO(n, n_steps=K, update_precision="tf32")
+model = PPO(n, n_steps=K, update_precision=mode)
 model.collect_rollouts()
 P = lambda t: None if t is None else C.c_void_p(t.data_ptr())
 dbg = torch.zeros(2 * 74 * 2 * 128 * 256, device='cuda')
@@ -22,7 +24,7 @@ for rep in range(3):
     _lib.check(model.lib.dronecu_ppo_adv_stats(model._h, P(b.adv), P(idx), 0, m, P(model._adv_stats), None))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    _lib.check(model.lib.dronecu_ppo_grad_tc(model._h, P(model.params), P(b.obs), P(b.actions), P(b.logp), P(b.adv), P(b.ret), P(idx), 0, m, 0.0, 1.0, P(model._adv_stats), P(model._grad), None))
+    _lib.check((model.lib.dronecu_ppo_grad_bf16 if mode == "bf16" else model.lib.dronecu_ppo_grad_tc)(model._h, P(model.params), P(b.obs), P(b.actions), P(b.logp), P(b.adv), P(b.ret), P(idx), 0, m, 0.0, 1.0, P(model._adv_stats), P(model._grad), None))
     e1.record(); torch.cuda.synchronize()
 print("kernel+reduce ms", e0.elapsed_time(e1), "tiles per WG", tiles_per_wg)
 t = dbg.cpu().numpy().view(np.int64)

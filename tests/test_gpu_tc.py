@@ -103,7 +103,8 @@ def _grad(model, index, m, first=0, tc=True):
     P = lambda t: None if t is None else C.c_void_p(t.data_ptr())
     model._adv_stats.zero_()
     _lib.check(model.lib.dronecu_ppo_adv_stats(model._h, P(b.adv), P(index), first, m, P(model._adv_stats), None))
-    fn = model.lib.dronecu_ppo_grad_tc if tc else model.lib.dronecu_ppo_grad
+    fn = {True: model.lib.dronecu_ppo_grad_tc, False: model.lib.dronecu_ppo_grad, "tf32": model.lib.dronecu_ppo_grad_tc,
+          "bf16": model.lib.dronecu_ppo_grad_bf16}[tc]
     _lib.check(fn(model._h, P(model.params), P(b.obs), P(b.actions), P(b.logp), P(b.adv), P(b.ret), P(index), first, m,
                   0.0, 1.0, P(model._adv_stats), P(model._grad), None))
     torch.cuda.synchronize()
@@ -140,9 +141,10 @@ def _separated_buffers(model, seed):
             f64(b.adv).reshape(-1), f64(b.ret).reshape(-1))
 
 
+@pytest.mark.parametrize("mode", ["tf32", "bf16"])
 @pytest.mark.parametrize("m", [128, 1000, 128 * 300 + 37, 128 * 2 * 148 * 3])
-def test_tc_minibatch_gradient(drl, m):
-    """tf32 tensor-core gradient vs float64 autograd of the oracle loss (and vs the fp32 CUDA-core kernel).
+def test_tc_minibatch_gradient(drl, m, mode):
+    """tensor-core gradient (all-tf32 kernel; kernel with bf16 weight-gradient operands) vs float64 autograd of the oracle loss (and vs the fp32 CUDA-core kernel).
     Stated tolerance: every parameter block within 1e-2 of its own largest entry (tf32 operands carry
     2^-11 relative rounding, MUFU tanh 2^-11; the sum over m samples averages part of it out), whole
     vector within 5e-3 of the largest entry; statistics as for the fp32 kernel but rtol 5e-3."""
@@ -154,7 +156,7 @@ def test_tc_minibatch_gradient(drl, m):
     obs, act, old_logp, adv, ret = _separated_buffers(model, 4)
     B = obs.shape[0]
     idx = torch.randperm(B, generator=torch.Generator().manual_seed(1))[:m]
-    g = _grad(model, idx.to(torch.int32).cuda(), m, tc=True)
+    g = _grad(model, idx.to(torch.int32).cuda(), m, tc=mode)
     g32 = _grad(model, idx.to(torch.int32).cuda(), m, tc=False)
     theta = model.params.cpu().double().requires_grad_(True)
     loss, stats = po.ppo_loss(theta, obs[idx], act[idx], old_logp[idx], adv[idx], ret[idx], ent_coef=0.01)
@@ -170,7 +172,7 @@ def test_tc_minibatch_gradient(drl, m):
         report.append(f"{name} {e:.2e} (vs fp32 kernel {e32:.2e})")
         if not e <= 1e-2:
             bad.append(name)
-    print(f"m={m}: " + "; ".join(report))
+    print(f"{mode} m={m}: " + "; ".join(report))
     assert not bad, f"blocks out of tolerance: {bad}: " + "; ".join(report)
     assert np.abs(g[:po.N_PARAMS] - ref).max() <= 5e-3 * scale
     st = g[po.N_PARAMS:]
@@ -179,7 +181,7 @@ def test_tc_minibatch_gradient(drl, m):
     np.testing.assert_allclose(st[1] / m, stats["value_loss"], rtol=5e-3)
     np.testing.assert_allclose(st[3] / m, stats["clip_fraction"], atol=2.0 / m)
     assert 0.2 < stats["clip_fraction"] < 0.6
-    again = _grad(model, idx.to(torch.int32).cuda(), m, tc=True)
+    again = _grad(model, idx.to(torch.int32).cuda(), m, tc=mode)
     assert np.array_equal(g, again)                       # fixed tile order + fixed-order reduction
     model.close()
 
@@ -201,7 +203,8 @@ def test_tc_update_trains_like_fp32(drl):
     assert (ps[0] - ps[1]).abs().max().item() < 2e-3
 
 
-def test_tc_gradient_is_race_free_under_repetition(drl):
+@pytest.mark.parametrize("mode", ["tf32", "bf16"])
+def test_tc_gradient_is_race_free_under_repetition(drl, mode):
     """40 back-to-back launches of the tensor-core gradient over the same ragged minibatch (several tiles per
     warpgroup, a partial last tile, an idle warpgroup tail) must be bit-identical: the kernel's hand-overs
     (mbarriers, tcgen05 fences, async-proxy fences) leave no window for a stale operand."""
@@ -213,8 +216,8 @@ def test_tc_gradient_is_race_free_under_repetition(drl):
     model.params.copy_(_rand_params(11, 0.5).float().cuda())
     _separated_buffers(model, 6)
     idx = torch.randperm(n * K, generator=torch.Generator().manual_seed(2))[:m].to(torch.int32).cuda()
-    first = _grad(model, idx, m, tc=True)
+    first = _grad(model, idx, m, tc=mode)
     assert np.isfinite(first).all() and np.abs(first).max() > 0
     for _ in range(40):
-        assert np.array_equal(_grad(model, idx, m, tc=True), first)
+        assert np.array_equal(_grad(model, idx, m, tc=mode), first)
     model.close()
