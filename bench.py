@@ -526,7 +526,7 @@ def main():
     ap.add_argument("--ppo-epochs", type=int, default=10)
     ap.add_argument("--ppo-minibatches", type=int, default=4)
     ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32"], help="policy MLP in the rollout: CUDA cores or tcgen05")
-    ap.add_argument("--update-precision", default=None, choices=["fp32", "tf32", "bf16"], help="PPO minibatch gradient: CUDA cores or tcgen05 (default: same as --precision)")
+    ap.add_argument("--update-precision", default="bf16", choices=["fp32", "tf32", "bf16"], help="PPO minibatch gradient: fp32 = CUDA cores (parity path), tf32 = tcgen05 all-tf32, bf16 = tcgen05 with bf16 weight-gradient operands, three tiles per SM (default)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
