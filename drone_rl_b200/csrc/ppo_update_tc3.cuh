@@ -14,9 +14,10 @@
 //     is simply [8-feature group][128 samples][16 bytes]: one conflict-free 16-byte store per group (probed on the
 //     B200 for A and B operands, N = 8 / 16 / 72: scratch/mma_probe_bf16.cu);
 //   * 54 KB of shared memory and 136 TMEM columns per tile: THREE compute warpgroups per CTA; the weight-gradient
-//     accumulators (96 columns) are shared by the three and therefore fed by ONE issuer thread, which serves the
-//     warpgroups in a fixed rotation, two steps apart (so that they sit in different phases, and so that the
-//     accumulation order -- hence every bit of the result -- does not depend on timing);
+//     accumulators (96 columns) are shared by the three and therefore fed by ONE thread (issuer warp 1: steps S4..S6),
+//     in a fixed rotation over the warpgroups, two steps apart (so that they sit in different phases, and so that the
+//     accumulation order -- hence every bit of the result -- does not depend on timing); a second issuer warp serves the
+//     steps that only touch a warpgroup's private columns (S1..S3), walking the same global order;
 //   * tanh'(layer 1) = 1 - H1^2 is stashed per sample as bf16 (2^-9 relative) next to the operands, because H1 itself
 //     survives only as a bf16 operand (1 - h^2 from a rounded h would lose the saturated units); tanh'(layer 2) uses
 //     the fp32 H2 still in TMEM.
@@ -33,7 +34,7 @@ using namespace tcu;            // descriptors, TMEM ld / st helpers, elect_one,
 
 constexpr int kWG3 = 3;
 constexpr int kComputeThreads3 = 128 * kWG3;
-constexpr int kThreads3 = kComputeThreads3 + 32;       // + ONE issuer warp
+constexpr int kThreads3 = kComputeThreads3 + 64;       // + TWO issuer warps: private steps (S1..S3) | accumulating steps (S4..S6)
 constexpr int kGrp = 128 * 16;                         // one 8-feature group of a bf16 MN-major operand: [128 samples][16 B]
 constexpr int kWgCols = 136;                           // P 64 | Q 64 | G 8
 constexpr int kCP = 0, kCQ = 64, kCG = 128;
@@ -56,7 +57,8 @@ struct alignas(1024) Smem3 {
   float b3[kAct];
   float log_std[kAct];
   float wsum[kWG3][4][kNS];
-  alignas(8) unsigned long long full[kWG3];
+  alignas(8) unsigned long long full[kWG3];     // operands of S1 / S2 / S3 staged (served by issuer warp 0)
+  alignas(8) unsigned long long fullA[kWG3];    // operands of S4 / S5 / S6 staged (served by issuer warp 1, fixed order)
   alignas(8) unsigned long long done[kWG3];
   uint32_t tmem_base, pad1[3];
 };
@@ -111,7 +113,7 @@ __device__ __forceinline__ void setup3(Smem3& S, const float* __restrict__ theta
     S.log_std[tid] = theta[O_LOGSTD + tid];
   }
   if (tid == 0) {
-    for (int w = 0; w < kWG3; ++w) { mbar_init(&S.full[w], 128); mbar_init(&S.done[w], 1); }
+    for (int w = 0; w < kWG3; ++w) { mbar_init(&S.full[w], 128); mbar_init(&S.fullA[w], 128); mbar_init(&S.done[w], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
@@ -129,6 +131,7 @@ __device__ __forceinline__ void setup3(Smem3& S, const float* __restrict__ theta
 // The issuer warp.  Virtual time v = 0, 1, 2 ...: at v, warpgroup w is served its step v - 2 w (if it has one) -- a
 // fixed rotation, so the three warpgroups run two steps apart and the shared accumulators see the tiles in an order
 // that does not depend on timing.
+template <int ROLE>      // 0: the private steps S1..S3 ; 1: the steps that add into the shared accumulators, S4..S6
 __device__ __forceinline__ void issuer3(Smem3& S, const int64_t n_tiles, const int64_t stride, long long* tlog) {
   // every descriptor is built once; a K slice, and the warpgroup, only bump the 14-bit start-address field (16-byte units).
   // The service code exists ONCE (w is a run-time value): unrolled per warpgroup it was 24 KB of straight-line code that
@@ -156,13 +159,17 @@ __device__ __forceinline__ void issuer3(Smem3& S, const int64_t n_tiles, const i
   for (int v = 0; v < vmax; ++v) {
 #pragma unroll 1
     for (int w = 0; w < kWG3; ++w) {
+      // both issuer warps walk the SAME global order (virtual time v, warpgroup w at its step v - 2 w) and each serves
+      // only its own steps: a service can only wait for services that precede it in that order, so the split cannot
+      // deadlock (an independent rotation per role did)
       const int sidx = v - 2 * w;
       const int nst = (w == 0) ? steps0 : (w == 1) ? steps1 : steps2;
       if (sidx < 0 || sidx >= nst) continue;
       const int step = (stp_pack >> (4 * w)) & 15;
       stp_pack = (stp_pack & ~(15u << (4 * w))) | ((uint32_t)(step == 5 ? 0 : step + 1) << (4 * w));
-      if (w == 0 && step == 0 && sidx > 0) ++tix;
-      mbar_wait(&S.full[w], (ph_mask >> w) & 1u);
+      if ((step >= 3) != (ROLE == 1)) continue;
+      if (w == 0 && (step == 0 || step == 3) && sidx > 2) ++tix;
+      mbar_wait(ROLE ? &S.fullA[w] : &S.full[w], (ph_mask >> w) & 1u);
       ph_mask ^= 1u << w;
       fence_after();
       if (w == 0) TSTAMP(tlog, tix, 2 * step);
@@ -222,12 +229,13 @@ __global__ void __launch_bounds__(tcb::kThreads3, 1) ppo_grad_bf16_kernel(const 
   const int64_t n_tiles = (A.m + 127) / 128;
   const int64_t stride = (int64_t)gridDim.x * kWG3;
 
-  if (warp == 4 * kWG3) {
+  if (warp >= 4 * kWG3) {
     long long* tlog = nullptr;
 #if DRONECU_TC_TIMING
     if (A.dbg != nullptr && blockIdx.x == 0 && tw == 0) tlog = reinterpret_cast<long long*>(A.dbg) + 1024;
 #endif
-    issuer3(S, n_tiles, stride, tlog);
+    if (warp == 4 * kWG3) issuer3<0>(S, n_tiles, stride, tlog);
+    else issuer3<1>(S, n_tiles, stride, tlog);
   } else {
     const int wg = tid >> 7, r = tid & 127, wq = r >> 5;
     float std_inv[kAct], logstd_sum = 0.f;
@@ -248,6 +256,7 @@ __global__ void __launch_bounds__(tcb::kThreads3, 1) ppo_grad_bf16_kernel(const 
     unsigned char* const rowG1 = S.XG[wg] + r * 128;       // 8 chunks of 16 B, chunk c at ((c ^ (r & 7)) << 4)
     const int sw = r & 7;
     unsigned long long* const full = &S.full[wg];
+    unsigned long long* const fullA = &S.fullA[wg];
     unsigned long long* const done = &S.done[wg];
     const uint32_t tmem = S.tmem_base + wg * kWgCols;
     const uint32_t tL = tmem + ((uint32_t)(wq * 32) << 16);
@@ -432,7 +441,7 @@ __global__ void __launch_bounds__(tcb::kThreads3, 1) ppo_grad_bf16_kernel(const 
         *reinterpret_cast<uint4*>(rowA + 8 * kGrp) = make_uint4(pack_bf16(g3[0], g3[1]), pack_bf16(g3[2], g3[3]), pack_bf16(one, 0.f), 0u);
       }
       wait_st();
-      hand_over(full);
+      hand_over(fullA);
       TSTAMP(tlog, it, 9);
 
       // ---------------- S4 done: dZ2 = dH2 * (1 - H2^2) -> Q (tf32, A of S5), bufB (bf16, A of S5's wgrad) ----------------
@@ -458,7 +467,7 @@ __global__ void __launch_bounds__(tcb::kThreads3, 1) ppo_grad_bf16_kernel(const 
         st16(tL + kCQ + 16 * c, d);
       }
       wait_st();
-      hand_over(full);
+      hand_over(fullA);
       TSTAMP(tlog, it, 11);
 
       // ---------------- S5 done: dZ1 = dH1 * (1 - H1^2) -> bufA (bf16, A of S6) ----------------
@@ -487,7 +496,7 @@ __global__ void __launch_bounds__(tcb::kThreads3, 1) ppo_grad_bf16_kernel(const 
           if (c < 3) ld_fence(w);
         }
       }
-      hand_over(full);                          // S6; awaited at the top of the next tile / after the loop
+      hand_over(fullA);                          // S6; awaited at the top of the next tile / after the loop
       TSTAMP(tlog, it, 13);
     }
     if (it > 0) { mbar_wait(done, ph); ph ^= 1; }
