@@ -27,7 +27,7 @@ struct dronecu_ppo {
   float* partials;   // [2 * n_sm, kGradLen] (the tensor-core kernel writes one vector per warpgroup)
   float* moments;    // [2, kParams]  Adam m | v
   double* adv_partials; // [n_sm * 8, 2]
-  int64_t step;
+  long long* d_step; // device-resident Adam step count (ppo_apply_kernel increments it)
   uint64_t launches;
   float* dbg;        // see dronecu_ppo_debug_buffer
 };
@@ -146,6 +146,8 @@ extern "C" int dronecu_ppo_create(const dronecu_ppo_config* cfg, int device, dro
   CUDA_TRY(cudaMalloc(&p->moments, sizeof(float) * 2 * kParams));
   CUDA_TRY(cudaMalloc(&p->adv_partials, sizeof(double) * 2 * (size_t)p->n_sm * 8));
   CUDA_TRY(cudaMemset(p->moments, 0, sizeof(float) * 2 * kParams));
+  CUDA_TRY(cudaMalloc(&p->d_step, sizeof(long long)));
+  CUDA_TRY(cudaMemset(p->d_step, 0, sizeof(long long)));
   CUDA_TRY(cudaFuncSetAttribute(ppo_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UpdSmem)));
   CUDA_TRY(cudaFuncSetAttribute(ppo_grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcUpdSmem));
   CUDA_TRY(cudaFuncSetAttribute(ppo_grad_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTc3Smem));
@@ -157,13 +159,19 @@ extern "C" int dronecu_ppo_destroy(dronecu_ppo* p) {
   if (!p) return DRONECU_OK;
   DeviceGuard guard(p->device);
   cudaDeviceSynchronize();
-  cudaFree(p->partials); cudaFree(p->moments); cudaFree(p->adv_partials);
+  cudaFree(p->partials); cudaFree(p->moments); cudaFree(p->adv_partials); cudaFree(p->d_step);
   cudaGetLastError();
   delete p;
   return DRONECU_OK;
 }
 
-extern "C" int64_t dronecu_ppo_num_updates(const dronecu_ppo* p) { return p ? p->step : 0; }
+extern "C" int64_t dronecu_ppo_num_updates(const dronecu_ppo* p) {      // synchronises the device (the count lives there)
+  if (!p) return 0;
+  DeviceGuard guard(p->device);
+  long long t = 0;
+  if (cudaMemcpy(&t, p->d_step, sizeof(t), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return (int64_t)t;
+}
 
 // host copy of Philox4x32-10 (philox.cuh is device code)
 static void philox_host(uint32_t c[4], uint32_t k0, uint32_t k1) {
@@ -282,14 +290,11 @@ extern "C" int dronecu_ppo_apply(dronecu_ppo* p, float* d_params, const float* d
                                  float* d_info, void* stream) {
   if (!p || !d_params || !d_grad || !(inv_count > 0)) return fail(DRONECU_ERR_INVALID, "dronecu_ppo_apply: bad argument");
   DeviceGuard guard(p->device);
-  p->step += 1;
-  const double b1 = p->cfg.beta1, b2 = p->cfg.beta2;
-  const double bc1 = 1.0 - std::pow(b1, (double)p->step), bc2 = 1.0 - std::pow(b2, (double)p->step);
   AdamArgs a;
   a.theta = d_params; a.grad = d_grad; a.m = p->moments; a.v = p->moments + kParams;
   a.inv_count = (float)inv_count;
-  a.lr_over_bc1 = (float)(p->cfg.learning_rate / bc1);
-  a.inv_sqrt_bc2 = (float)(1.0 / std::sqrt(bc2));
+  a.lr = p->cfg.learning_rate;
+  a.step = p->d_step;
   a.beta1 = p->cfg.beta1; a.beta2 = p->cfg.beta2; a.eps = p->cfg.adam_eps; a.max_norm = p->cfg.max_grad_norm;
   a.info = d_info;
   ppo_apply_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(a);
@@ -303,7 +308,12 @@ extern "C" int dronecu_ppo_get_state(dronecu_ppo* p, float* d_moments, int64_t* 
   DeviceGuard guard(p->device);
   if (d_moments)
     CUDA_TRY(cudaMemcpyAsync(d_moments, p->moments, sizeof(float) * 2 * kParams, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
-  if (h_step) *h_step = p->step;
+  if (h_step) {
+    long long t = 0;
+    CUDA_TRY(cudaMemcpyAsync(&t, p->d_step, sizeof(t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    *h_step = (int64_t)t;
+  }
   return DRONECU_OK;
 }
 
@@ -312,6 +322,8 @@ extern "C" int dronecu_ppo_set_state(dronecu_ppo* p, const float* d_moments, int
   DeviceGuard guard(p->device);
   if (d_moments)
     CUDA_TRY(cudaMemcpyAsync(p->moments, d_moments, sizeof(float) * 2 * kParams, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
-  p->step = step;
+  const long long t = step;
+  CUDA_TRY(cudaMemcpyAsync(p->d_step, &t, sizeof(t), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
   return DRONECU_OK;
 }

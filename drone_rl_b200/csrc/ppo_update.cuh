@@ -417,14 +417,22 @@ __global__ void adv_stats_finish_kernel(const double* __restrict__ partial, int 
 struct AdamArgs {
   float* theta; const float* grad; float* m; float* v;
   float inv_count;           // 1 / (global number of samples in the minibatch)
-  float lr_over_bc1, inv_sqrt_bc2, beta1, beta2, eps, max_norm;
+  float lr, beta1, beta2, eps, max_norm;
+  long long* step;           // device-resident Adam step count (incremented here: the launch sequence is CUDA-graph capturable)
   float* info;               // [kStats + 1]: mean statistics + pre-clip gradient norm
 };
 
 // torch.nn.utils.clip_grad_norm_(max_norm) + torch.optim.Adam.step() on the flat vector (one CTA)
 __global__ void __launch_bounds__(1024) ppo_apply_kernel(const AdamArgs A) {
   __shared__ float red[32];
-  __shared__ float coef_s;
+  __shared__ float coef_s, lr_over_bc1_s, inv_sqrt_bc2_s;
+  if (threadIdx.x == 0) {      // torch.optim.Adam bias corrections of step t = ++(*step)
+    const long long t = *A.step + 1;
+    *A.step = t;
+    const double bc1 = 1.0 - pow((double)A.beta1, (double)t), bc2 = 1.0 - pow((double)A.beta2, (double)t);
+    lr_over_bc1_s = (float)((double)A.lr / bc1);
+    inv_sqrt_bc2_s = (float)(1.0 / sqrt(bc2));
+  }
   float sq = 0.f;
   for (int i = threadIdx.x; i < kParams; i += blockDim.x) {
     const float g = A.grad[i] * A.inv_count;
@@ -447,12 +455,13 @@ __global__ void __launch_bounds__(1024) ppo_apply_kernel(const AdamArgs A) {
   }
   __syncthreads();
   const float coef = coef_s * A.inv_count;
+  const float lr_over_bc1 = lr_over_bc1_s, inv_sqrt_bc2 = inv_sqrt_bc2_s;
   for (int i = threadIdx.x; i < kParams; i += blockDim.x) {
     const float g = A.grad[i] * coef;
     const float m = A.beta1 * A.m[i] + (1.0f - A.beta1) * g;
     const float v = A.beta2 * A.v[i] + (1.0f - A.beta2) * g * g;
     A.m[i] = m; A.v[i] = v;
-    A.theta[i] -= A.lr_over_bc1 * m / (sqrtf(v) * A.inv_sqrt_bc2 + A.eps);
+    A.theta[i] -= lr_over_bc1 * m / (sqrtf(v) * inv_sqrt_bc2 + A.eps);
   }
 }
 

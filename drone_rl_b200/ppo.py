@@ -98,7 +98,7 @@ class PPO:
                  gae_lambda: float = 0.95, clip_range: float = 0.2, ent_coef: float = 0.0, vf_coef: float = 0.5,
                  max_grad_norm: float = 0.5, learning_rate: float = 3e-4, normalize_advantage: bool = True,
                  seed: int = 0, device: int = 0, verbose: int = 0, policy_seed: Optional[int] = None,
-                 rollout_precision: str = "fp32", update_precision: str = "fp32"):
+                 rollout_precision: str = "fp32", update_precision: str = "fp32", cuda_graph: Optional[bool] = None):
         self.lib = _lib.load()
         self.rank, self.world = 0, 1
         if torch.distributed.is_available() and torch.distributed.is_initialized():
@@ -135,6 +135,11 @@ class PPO:
         self.num_timesteps, self.n_updates = 0, 0
         self._perm, self._epochs_done = None, 0
         self.grad_events = None                   # set to [] to collect (start, end, samples) events per gradient launch
+        # One epoch's minibatch sequence (adv-stats -> grad -> reduce -> clip+Adam, x minibatches) as ONE CUDA graph: with
+        # SB3's defaults (batch 64) an epoch is hundreds of 10-microsecond kernels and the host launch rate is the bound.
+        # Default: on for small minibatches on a single GPU (NCCL all-reduces stay outside graphs here).
+        self.cuda_graph = cuda_graph
+        self._graph, self._graph_key, self._graph_launches = None, None, 0
         self.logger_values: dict = {}
         self.launches = 0
         self.batch.reset()          # SB3 _setup_learn: env.reset()  (ep_num 1 -> 2)
@@ -196,6 +201,25 @@ class PPO:
         self.launches += 3
         self.n_updates += 1
 
+    def _epoch_graph(self, perm: torch.Tensor, B: int):
+        """Replay (capture on first use) the CUDA graph of one epoch over the index buffer `perm`."""
+        key = (perm.data_ptr(), B, self.batch_size, self.normalize_advantage, self.update_precision)
+        if self._graph is None or self._graph_key != key:
+            torch.cuda.synchronize(self.device)
+            l0, u0 = self.launches, self.n_updates
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for start in range(0, B, self.batch_size):
+                    m = min(self.batch_size, B - start)
+                    self._minibatch(perm[start:start + m], 0, m)
+            # capture does not execute: undo the bookkeeping of the capture pass, remember it per replay
+            self._graph_launches, self._graph_updates = self.launches - l0, self.n_updates - u0
+            self.launches, self.n_updates = l0, u0
+            self._graph, self._graph_key = g, key
+        self._graph.replay()
+        self.launches += self._graph_launches
+        self.n_updates += self._graph_updates
+
     def train(self):
         """SB3 PPO.train(): n_epochs passes over the buffer in random minibatches of batch_size."""
         B = self.n_steps * self.n_envs
@@ -208,6 +232,10 @@ class PPO:
                                                               _ptr(perm), _stream_ptr(self.device)), "dronecu_minibatch_permutation")
             self._epochs_done += 1
             self.launches += 1
+            use_graph = self.cuda_graph if self.cuda_graph is not None else (self.batch_size <= 16384 and B // self.batch_size >= 4)
+            if use_graph and self.world == 1 and self.grad_events is None:
+                self._epoch_graph(perm, B)
+                continue
             for start in range(0, B, self.batch_size):
                 m = min(self.batch_size, B - start)
                 self._minibatch(perm[start:start + m], 0, m)

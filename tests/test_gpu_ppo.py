@@ -317,3 +317,25 @@ def test_minibatch_permutation_matches_oracle(drl, n):
         seen.append(got)
     if n > 64:
         assert (seen[0] == seen[1]).mean() < 0.01 and abs(np.corrcoef(np.arange(n), seen[0])[0, 1]) < 0.05
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_cuda_graph_epoch_equals_eager(drl, prec):
+    """One epoch of minibatch steps replayed as a CUDA graph == the same launches issued one by one: bit-identical
+    parameters, Adam moments and step count (the Adam step lives on the device so that the sequence is capturable)."""
+    from drone_rl_b200.ppo import PPO
+    out = []
+    for graph in (False, True):
+        m = PPO(drl.DroneBatch(64, drl.EnvConfig.single(), seed=5), n_steps=32, batch_size=64, n_epochs=3, seed=5,
+                update_precision=prec, cuda_graph=graph)
+        for _ in range(2):
+            m.collect_rollouts()
+            m.train()
+        torch.cuda.synchronize()
+        sd = m.state_dict()
+        assert m.n_updates == 2 * 3 * 32 and sd["adam_step"] == m.n_updates
+        assert (m._graph is not None) == graph
+        out.append((m.params.clone(), sd["adam"].clone(), dict(m.logger_values)))
+        m.close()
+    assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1])
+    assert out[0][2]["train/value_loss"] == out[1][2]["train/value_loss"]
