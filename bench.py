@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- env-steps/s of the fused quadcopter env step on B200 (BASELINE.json metric).
 
-    python bench.py --gpus N --steps K --warmup W [--workload c4|c2|k1] [--impl reference]
+    python bench.py --gpus N --steps K --warmup W [--workload c4|c2|k1|c3|c5|c1] [--impl reference]
 
 One bench "step" = ONE launch of the fused kernel: `fuse` consecutive env steps over the rank's
 shard of envs, state in registers, the full rollout record (next obs, action, reward, done)
@@ -15,6 +15,9 @@ Workloads (BASELINE.json configs):
                 in-kernel Philox random actions, fuse=32.
   c2            configs[1]: 4096 envs x 1000 steps, random actions streamed from HBM, one launch.
   k1            the SB3-style boundary: one env step per launch (dronecu_step), 8M envs.
+  c3            configs[2]: 1,048,576 envs, fused K-step rollout with the PPO MLP policy forward in-kernel (tcgen05).
+  c5            configs[4]: full PPO iteration (rollout + GAE + 10 epochs x 4 minibatches), NCCL gradient all-reduce for N > 1.
+  c1            configs[0]: the reference's own shape (1 env, n_steps 2048, batch 64, 10 epochs) -- latency-bound.
 
 --impl reference times the reference's CPU implementation of the same path (the numpy port in
 oracle/ -- /root/reference is Python and cannot travel to the GPU box) on all host cores.
@@ -157,7 +160,7 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    if args.workload in ("c3", "c5"):
+    if args.workload in ("c3", "c5", "c1"):
         return run_reference_ppo(args, cores)
     k_inner = 8
     cb = CpuBaseline(cores)
@@ -183,12 +186,16 @@ def run_reference(args):
 PPO_CPU_SAMPLE = dict(n_envs=4096, n_steps=32, n_epochs=10, minibatches=4)
 
 
-def time_cpu_ppo(update, budget_s=10.0):
+def time_cpu_ppo(update, budget_s=10.0, reference_shape=False):
     """The restated-SB3 CPU loop (oracle/ppo_loop.py, torch CPU with all host threads + the numpy env port):
     (a) batched the way this repo's workload is, (b) exactly as the reference runs it (train.py:33-43:
     one env, n_steps 2048, batch 64, 10 epochs)."""
     import torch
     from oracle import ppo_loop
+    if reference_shape:
+        v1, its1, dt1 = ppo_loop.time_loop(1, 2048, 64, 10, budget_s=2 * budget_s, update=True)
+        return v1, (f"restated SB3 loop on CPU (torch {torch.get_num_threads()} threads + numpy env port), the reference's own "
+                    f"config: 1 env, n_steps 2048, batch 64, 10 epochs; {its1} iterations in {dt1:.1f}s")
     c = PPO_CPU_SAMPLE
     v, its, dt = ppo_loop.time_loop(c["n_envs"], c["n_steps"], c["n_envs"] * c["n_steps"] // c["minibatches"],
                                     c["n_epochs"], budget_s=budget_s, update=update)
@@ -203,8 +210,8 @@ def time_cpu_ppo(update, budget_s=10.0):
 
 def run_reference_ppo(args, cores):
     from oracle import ppo_loop
-    c = PPO_CPU_SAMPLE
-    update = args.workload == "c5"
+    c = PPO_CPU_SAMPLE if args.workload != "c1" else dict(n_envs=1, n_steps=2048, n_epochs=10, minibatches=32)
+    update = args.workload != "c3"
     loop = ppo_loop.PPOLoopOracle(c["n_envs"], c["n_steps"], c["n_envs"] * c["n_steps"] // c["minibatches"], c["n_epochs"])
 
     def one():
@@ -236,6 +243,7 @@ WORKLOAD_NAMES = {
     "k1": "SB3 boundary: one env step per launch (dronecu_step), 8388608 envs/GPU, streamed actions",
     "c3": "configs[2]: 1048576 envs fused K-step rollout with the PPO MLP policy/value forward in-kernel",
     "c5": "configs[4]: full PPO loop (in-kernel-policy rollout + GAE + 10-epoch minibatch update, NCCL grad all-reduce)",
+    "c1": "configs[0]: the reference's own shape -- ONE env, n_steps 2048, batch 64, 10 epochs (train.py defaults), full PPO loop",
 }
 
 
@@ -406,7 +414,7 @@ def run_ppo(args):
 
     def one_step():
         model.collect_rollouts()
-        if wl == "c5":
+        if wl in ("c5", "c1"):
             model.train()
 
     def barrier():
@@ -419,7 +427,7 @@ def run_ppo(args):
     barrier()
     l0 = env.launch_count + model.launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    model.grad_events = [] if wl == "c5" else None
+    model.grad_events = [] if wl == "c5" else None        # c1 keeps the CUDA-graph path (no per-launch events inside a graph)
     roll_events = []
     with ClockSampler(local) as clocks:
         ev0.record()
@@ -434,7 +442,9 @@ def run_ppo(args):
         ev1.record()
         barrier()
     # the dominant kernel of the workload, timed live by CUDA events on the launching stream
-    if wl == "c5":
+    if wl == "c1":
+        ms, units, kflop, kname = [ev0.elapsed_time(ev1) / args.steps], float(n * K), 20864.0 * (1 + 3 * args.ppo_epochs), "whole iteration (latency-bound: 2048 sequential env steps + one CUDA graph per epoch)"
+    elif wl == "c5":
         ms = [a.elapsed_time(b) for a, b, _ in model.grad_events]
         units = float(np.mean([m for _, _, m in model.grad_events]))
         up = args.update_precision or args.precision
@@ -466,7 +476,7 @@ def run_ppo(args):
         its = max(1, min(args.steps, 5))
         barrier()
         t0 = time.perf_counter()
-        if wl == "c5":
+        if wl in ("c5", "c1"):
             model.num_timesteps = 0
             model.learn(total_timesteps=its * n * K * world)
             d2h = 9 * 4 + 128 * 64
@@ -481,7 +491,7 @@ def run_ppo(args):
         if world > 1:
             dist.all_reduce(td, op=dist.ReduceOp.MAX)
         e2e = {"value": its * n * K * world / float(td.item()), "unit": "env-steps/s", "h2d_bytes_per_step": 0,
-               "d2h_bytes_per_step": d2h, "api": "PPO.learn" if wl == "c5" else "PPO.collect_rollouts + episode_stats",
+               "d2h_bytes_per_step": d2h, "api": "PPO.learn" if wl in ("c5", "c1") else "PPO.collect_rollouts + episode_stats",
                "iterations": its, "note": "GPU-resident simulator: no host inputs per iteration; the result read back is the "
                "episode statistics (128 slots x 64 B)" + (" and the train/* scalars" if wl == "c5" else "")}
     if rank == 0:
@@ -491,7 +501,8 @@ def run_ppo(args):
                 "config": {"workload": WORKLOAD_NAMES[wl], "envs_per_gpu": n, "n_steps": K, "n_epochs": args.ppo_epochs,
                            "minibatches_per_epoch": args.ppo_minibatches, "policy": "MlpPolicy 15-64-64-{4,1} tanh, random init", "rollout_precision": args.precision,
                            "update_precision": args.update_precision or args.precision,
-                           "l2": "rollout buffers %.1f GB per iteration, larger than L2" % (n * K * 93 / 1e9)},
+                           "l2": ("rollout buffers %.1f GB per iteration, larger than L2" % (n * K * 93 / 1e9)) if wl != "c1" else
+                           "latency-bound workload (190 KB of buffers): no L2 effect to flush"},
                 "roofline": {"bound": "tensor", "achieved": k_tflops, "peak": peak, "unit": "TFLOP/s", "frac": k_tflops / peak,
                              "traffic": None, "kernel": kname, "avg_launch_ms": k_ms, "units_per_launch": units,
                              "algorithmic_flop_per_unit": kflop, "whole_step_tflops": achieved, "note": ("tcgen05 kind::tf32 MMAs (tf32 dense peak = half the bf16 peak used as the "
@@ -501,7 +512,7 @@ def run_ppo(args):
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks.summary(),
                 "train": {k: v for k, v in model.logger_values.items() if k.startswith("train/")}}
         if world == 1 and not args.no_cpu:
-            v, sample = time_cpu_ppo(update=(wl == "c5"))
+            v, sample = time_cpu_ppo(update=(wl != "c3"), reference_shape=(wl == "c1"))
             line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": os.cpu_count() or 1, "kind": "port", "sample": sample}
         print(json.dumps(line), flush=True)
     model.close()
@@ -531,7 +542,9 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)
-    elif args.workload in ("c3", "c5"):
+    elif args.workload in ("c3", "c5", "c1"):
+        if args.workload == "c1":          # reference train.py:12-16, :36-43
+            args.ppo_envs, args.fuse, args.ppo_minibatches, args.ppo_epochs = 1, 2048, 32, 10
         run_ppo(args)
     else:
         run_gpu(args)
