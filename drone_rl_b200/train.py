@@ -150,7 +150,10 @@ def main(argv=None):
     ap.add_argument("--n-epochs", type=int, default=10)
     ap.add_argument("--learning-rate", type=float, default=3e-4)
     ap.add_argument("--seed", type=int, default=0)
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32"])
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32"], help="policy MLP in the rollout: CUDA cores (parity path) or tcgen05")
+    ap.add_argument("--update-precision", default=None, choices=["fp32", "tf32", "bf16"],
+                    help="minibatch gradient: fp32 CUDA cores, tcgen05 all-tf32, or tcgen05 with bf16 weight-gradient operands "
+                         "(default: fp32 with --precision fp32, bf16 with --precision tf32)")
     ap.add_argument("--tensorboard-root", default="./tensorboard")
     ap.add_argument("--save", default="ppo_drone_rel_obs_pos_reward")
     ap.add_argument("--quiet", action="store_true")
@@ -170,7 +173,8 @@ def main(argv=None):
     n_steps = args.n_steps or max(1, 2048 // args.n_envs)
     env = DroneBatch(args.n_envs, EnvConfig.single(), device=local, seed=args.seed, env_offset=rank * args.n_envs)
     kw = dict(n_steps=n_steps, batch_size=args.batch_size, learning_rate=args.learning_rate, n_epochs=args.n_epochs,
-              seed=args.seed, rollout_precision=args.precision, update_precision=args.precision)
+              seed=args.seed, rollout_precision=args.precision,
+              update_precision=args.update_precision or ("bf16" if args.precision == "tf32" else "fp32"))
     if os.path.exists(args.resume):
         model = PPO.load(args.resume, env, **kw)
         if rank == 0:
