@@ -50,6 +50,9 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 #ifndef DRONECU_EMIT_BULK
 #define DRONECU_EMIT_BULK 0
 #endif
+#ifndef DRONECU_PIPE_PHILOX
+#define DRONECU_PIPE_PHILOX 1   // issue the action Philox block one step ahead (A/B knob)
+#endif
 #ifndef DRONECU_MIN_BLOCKS
 #define DRONECU_MIN_BLOCKS 3   // <= 80 registers/thread, 3 CTAs of 256 threads per SM: no spills and no per-step
                                // re-derivation of indices (at 64 registers ptxas did both); A/B in profiles/README.md
@@ -151,6 +154,10 @@ __global__ void __launch_bounds__(kBlock, DRONECU_MIN_BLOCKS) rollout_kernel(con
 
   float4 act = make_float4(0.f, 0.f, 0.f, 0.f);
   if (ACT_MODE == 0 && active) act = ld_quad_nc(A.actions + i);
+  // in-kernel actions: the Philox block of step k + 1 does not depend on the state, so it is issued one step ahead --
+  // its 40-deep dependency chain interleaves with the dynamics of step k instead of preceding them (ILP at 24 warps/SM)
+  uint4 wnext = make_uint4(0u, 0u, 0u, 0u);
+  if constexpr (ACT_MODE == 1) wnext = env_stream(P.keys, P.env_offset + (uint64_t)i, A.t0, STREAM_ACTION);
 
   size_t koff = 0;                                   // k * n: uniform, the base of step k in every [K,n,...] output
   for (int k = 0; k < A.K; ++k, koff += n) {
@@ -158,7 +165,12 @@ __global__ void __launch_bounds__(kBlock, DRONECU_MIN_BLOCKS) rollout_kernel(con
     if constexpr (ACT_MODE == 0) {
       if (active && k + 1 < A.K) act = ld_quad_nc(A.actions + koff + n + i);     // software prefetch of the next quad
     } else {
+#if DRONECU_PIPE_PHILOX
+      const uint4 w = wnext;
+      if (k + 1 < A.K) wnext = env_stream(P.keys, P.env_offset + (uint64_t)i, A.t0 + (uint64_t)(k + 1), STREAM_ACTION);
+#else
       const uint4 w = env_stream(P.keys, P.env_offset + (uint64_t)i, A.t0 + (uint64_t)k, STREAM_ACTION);
+#endif
       f = make_float4((float)(w.x >> 8) * act_scale, (float)(w.y >> 8) * act_scale,
                       (float)(w.z >> 8) * act_scale, (float)(w.w >> 8) * act_scale);
     }
