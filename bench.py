@@ -522,6 +522,9 @@ def run_ppo(args):
 
 
 def main():
+    # NCCL prints its version banner on STDOUT when NCCL_DEBUG=VERSION (some images export it): keep stdout = the JSON line
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
