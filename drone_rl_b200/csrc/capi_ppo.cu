@@ -215,6 +215,24 @@ extern "C" int dronecu_ppo_adv_stats(dronecu_ppo* p, const float* d_adv, const i
   return DRONECU_OK;
 }
 
+extern "C" int dronecu_ppo_adv_stats_epoch(dronecu_ppo* p, const float* d_adv, const int32_t* d_index, int64_t B,
+                                           int64_t batch, double* d_out, void* stream) {
+  if (!p || !d_adv || !d_out || B <= 0 || batch <= 0) return fail(DRONECU_ERR_INVALID, "dronecu_ppo_adv_stats_epoch: bad argument");
+  DeviceGuard guard(p->device);
+  const int64_t n_mb = (B + batch - 1) / batch;
+  if (n_mb > 65535) return fail(DRONECU_ERR_INVALID, "dronecu_ppo_adv_stats_epoch: more than 65535 minibatches per epoch");
+  // partials share adv_partials ([n_sm * 8, 2] doubles): gx CTAs per minibatch
+  const int64_t cap = (int64_t)p->n_sm * 8;
+  const unsigned gx = (unsigned)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>((batch + 255) / 256, cap / n_mb), (int64_t)p->n_sm * 4));
+  if ((int64_t)gx * n_mb > cap) return fail(DRONECU_ERR_INVALID, "dronecu_ppo_adv_stats_epoch: too many minibatches for the scratch buffer");
+  adv_stats_epoch_kernel<<<dim3(gx, (unsigned)n_mb), 256, 0, (cudaStream_t)stream>>>(d_adv, d_index, B, batch, p->adv_partials);
+  CUDA_TRY(cudaGetLastError());
+  adv_stats_epoch_finish_kernel<<<(unsigned)n_mb, 32, 0, (cudaStream_t)stream>>>(p->adv_partials, (int)gx, B, batch, d_out);
+  p->launches += 2;
+  CUDA_TRY(cudaGetLastError());
+  return DRONECU_OK;
+}
+
 static int ppo_grad_impl(dronecu_ppo* p, const float* d_params, const float* d_obs, const float* d_actions,
                          const float* d_old_logp, const float* d_adv, const float* d_returns,
                          const int32_t* d_index, int64_t first, int64_t m, float adv_mean, float adv_inv_std,

@@ -414,6 +414,41 @@ __global__ void adv_stats_finish_kernel(const double* __restrict__ partial, int 
   if (threadIdx.x == 0) { out[0] += s; out[1] += q; out[2] += (double)m; }
 }
 
+// the same statistics for EVERY minibatch of an epoch in two launches: minibatch b = positions [b * batch, min((b + 1) *
+// batch, B)) of the epoch's index array.  grid (gx, n_mb); partial [n_mb][gx][2]; out [n_mb][3] is WRITTEN.
+__global__ void adv_stats_epoch_kernel(const float* __restrict__ adv, const int32_t* __restrict__ index, int64_t B,
+                                       int64_t batch, double* __restrict__ partial) {
+  __shared__ double sh[2][8];
+  const int64_t lo = (int64_t)blockIdx.y * batch, hi = min(lo + batch, B);
+  double s = 0.0, q = 0.0;
+  for (int64_t p = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < hi; p += (int64_t)gridDim.x * blockDim.x) {
+    const double a = (double)adv[index ? (int64_t)index[p] : p];
+    s += a; q += a * a;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = s; sh[1][threadIdx.x >> 5] = q; }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh[threadIdx.x][w];
+    partial[2 * ((size_t)blockIdx.y * gridDim.x + blockIdx.x) + threadIdx.x] = t;
+  }
+}
+
+__global__ void adv_stats_epoch_finish_kernel(const double* __restrict__ partial, int gx, int64_t B, int64_t batch,
+                                              double* __restrict__ out) {
+  const double* p0 = partial + 2 * (size_t)blockIdx.x * gx;
+  double s = 0.0, q = 0.0;
+  for (int p = threadIdx.x; p < gx; p += 32) { s += p0[2 * p]; q += p0[2 * p + 1]; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+  if (threadIdx.x == 0) {
+    const int64_t lo = (int64_t)blockIdx.x * batch;
+    out[3 * blockIdx.x] = s; out[3 * blockIdx.x + 1] = q; out[3 * blockIdx.x + 2] = (double)(min(lo + batch, B) - lo);
+  }
+}
+
 struct AdamArgs {
   float* theta; const float* grad; float* m; float* v;
   float inv_count;           // 1 / (global number of samples in the minibatch)

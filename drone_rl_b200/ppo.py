@@ -140,6 +140,8 @@ class PPO:
         # Default: on for small minibatches on a single GPU (NCCL all-reduces stay outside graphs here).
         self.cuda_graph = cuda_graph
         self._graph, self._graph_key, self._graph_launches = None, None, 0
+        self._ep_stats = None
+        self._max_mb = 8 * torch.cuda.get_device_properties(self.device).multi_processor_count
         self.logger_values: dict = {}
         self.launches = 0
         self.batch.reset()          # SB3 _setup_learn: env.reset()  (ep_num 1 -> 2)
@@ -172,10 +174,14 @@ class PPO:
         self.num_timesteps += K * n * self.world
 
     # -- update -------------------------------------------------------------------------------------
-    def _minibatch(self, index: Optional[torch.Tensor], first: int, m: int):
+    def _minibatch(self, index: Optional[torch.Tensor], first: int, m: int, stats: Optional[torch.Tensor] = None):
+        """One optimiser step.  `stats`: this minibatch's (already all-reduced) [sum, sumsq, count] of the advantages
+        (train() computes them for the whole epoch at once); None: computed here."""
         b, st = self.buf, _stream_ptr(self.device)
         stats_ptr = None
-        if self.normalize_advantage:
+        if self.normalize_advantage and stats is not None:
+            stats_ptr = _ptr(stats)
+        elif self.normalize_advantage:
             self._adv_stats.zero_()
             _lib.check(self.lib.dronecu_ppo_adv_stats(self._h, _ptr(b.adv), _ptr(index), first, m,
                                                       _ptr(self._adv_stats), st), "dronecu_ppo_adv_stats")
@@ -201,17 +207,18 @@ class PPO:
         self.launches += 3
         self.n_updates += 1
 
-    def _epoch_graph(self, perm: torch.Tensor, B: int):
+    def _epoch_graph(self, perm: torch.Tensor, B: int, ep_stats: Optional[torch.Tensor] = None):
         """Replay (capture on first use) the CUDA graph of one epoch over the index buffer `perm`."""
-        key = (perm.data_ptr(), B, self.batch_size, self.normalize_advantage, self.update_precision)
+        key = (perm.data_ptr(), B, self.batch_size, self.normalize_advantage, self.update_precision,
+               None if ep_stats is None else ep_stats.data_ptr())
         if self._graph is None or self._graph_key != key:
             torch.cuda.synchronize(self.device)
             l0, u0 = self.launches, self.n_updates
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                for start in range(0, B, self.batch_size):
+                for k, start in enumerate(range(0, B, self.batch_size)):
                     m = min(self.batch_size, B - start)
-                    self._minibatch(perm[start:start + m], 0, m)
+                    self._minibatch(perm[start:start + m], 0, m, None if ep_stats is None else ep_stats[k])
             # capture does not execute: undo the bookkeeping of the capture pass, remember it per replay
             self._graph_launches, self._graph_updates = self.launches - l0, self.n_updates - u0
             self.launches, self.n_updates = l0, u0
@@ -232,13 +239,25 @@ class PPO:
                                                               _ptr(perm), _stream_ptr(self.device)), "dronecu_minibatch_permutation")
             self._epochs_done += 1
             self.launches += 1
+            # advantage statistics of EVERY minibatch of the epoch: two launches and (data parallel) one all-reduce per epoch
+            n_mb = (B + self.batch_size - 1) // self.batch_size
+            ep_stats = None
+            if self.normalize_advantage and n_mb <= self._max_mb:
+                if self._ep_stats is None or self._ep_stats.shape[0] != n_mb:
+                    self._ep_stats = torch.zeros(n_mb, 3, dtype=torch.float64, device=self.device)
+                ep_stats = self._ep_stats
+                _lib.check(self.lib.dronecu_ppo_adv_stats_epoch(self._h, _ptr(self.buf.adv), _ptr(perm), B, self.batch_size,
+                                                                _ptr(ep_stats), _stream_ptr(self.device)), "dronecu_ppo_adv_stats_epoch")
+                self.launches += 2
+                if self.world > 1:
+                    torch.distributed.all_reduce(ep_stats)
             use_graph = self.cuda_graph if self.cuda_graph is not None else (self.batch_size <= 16384 and B // self.batch_size >= 4)
             if use_graph and self.world == 1 and self.grad_events is None:
-                self._epoch_graph(perm, B)
+                self._epoch_graph(perm, B, ep_stats)
                 continue
-            for start in range(0, B, self.batch_size):
+            for k, start in enumerate(range(0, B, self.batch_size)):
                 m = min(self.batch_size, B - start)
-                self._minibatch(perm[start:start + m], 0, m)
+                self._minibatch(perm[start:start + m], 0, m, None if ep_stats is None else ep_stats[k])
         info = self._info.cpu().numpy()
         self.logger_values.update({"train/policy_gradient_loss": float(info[0]), "train/value_loss": float(info[1]),
                                    "train/approx_kl": float(info[2]), "train/clip_fraction": float(info[3]),

@@ -253,6 +253,12 @@ int dronecu_minibatch_permutation(int device, int64_t n, uint64_t seed, uint64_t
 int dronecu_ppo_adv_stats(dronecu_ppo* ppo, const float* d_adv, const int32_t* d_index, int64_t first, int64_t m,
                           double* d_out, void* stream);
 
+/* The same statistics for every minibatch of an epoch in two launches: minibatch b = rows d_index[b * batch ..
+ * min((b + 1) * batch, B)) (rows themselves when d_index is NULL); d_out[n_mb][3] is WRITTEN ([sum, sumsq, count] per
+ * minibatch; all-reduce the whole array once per epoch for data-parallel training).  At most n_sm * 8 minibatches. */
+int dronecu_ppo_adv_stats_epoch(dronecu_ppo* ppo, const float* d_adv, const int32_t* d_index, int64_t B, int64_t batch,
+                                double* d_out, void* stream);
+
 /* Forward + backward of one minibatch: d_grad[DRONECU_GRAD_LEN] = SUM over the minibatch of the
  * per-sample loss gradient (clipped surrogate + vf_coef * value MSE + ent_coef * entropy), followed by
  * the sums of: policy loss, squared value error, approx_kl, clip fraction, sample count.  Advantages

@@ -339,3 +339,30 @@ def test_cuda_graph_epoch_equals_eager(drl, prec):
         m.close()
     assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1])
     assert out[0][2]["train/value_loss"] == out[1][2]["train/value_loss"]
+
+
+def test_epoch_advantage_statistics(drl):
+    """The statistics of every minibatch of an epoch in one call == the per-minibatch entry point == numpy, incl. a
+    ragged last minibatch; count column exact."""
+    import ctypes as C
+    from drone_rl_b200 import _lib
+    from drone_rl_b200.ppo import PPO
+    model = PPO(drl.DroneBatch(96, drl.EnvConfig.single(), seed=2), n_steps=21, seed=2)
+    B, bs = 96 * 21, 500                                   # 4 full minibatches + one of 16
+    adv = torch.randn(B, device="cuda") * 3 + 0.5
+    perm = torch.randperm(B, device="cuda").to(torch.int32)
+    n_mb = (B + bs - 1) // bs
+    out = torch.zeros(n_mb, 3, dtype=torch.float64, device="cuda")
+    P = lambda t: C.c_void_p(t.data_ptr())
+    _lib.check(model.lib.dronecu_ppo_adv_stats_epoch(model._h, P(adv), P(perm), B, bs, P(out), None))
+    one = torch.zeros(3, dtype=torch.float64, device="cuda")
+    for k in range(n_mb):
+        m = min(bs, B - k * bs)
+        one.zero_()
+        _lib.check(model.lib.dronecu_ppo_adv_stats(model._h, P(adv), P(perm[k * bs:]), 0, m, P(one), None))
+        a = adv[perm[k * bs:k * bs + m].long()].double().cpu().numpy()
+        got = out[k].cpu().numpy()
+        assert got[2] == m == one[2].item()
+        np.testing.assert_allclose(got[:2], [a.sum(), (a * a).sum()], rtol=1e-12)
+        np.testing.assert_allclose(got[:2], one[:2].cpu().numpy(), rtol=1e-13)
+    model.close()
