@@ -142,7 +142,7 @@ def _separated_buffers(model, seed):
 
 
 @pytest.mark.parametrize("mode", ["tf32", "bf16"])
-@pytest.mark.parametrize("m", [128, 1000, 128 * 300 + 37, 128 * 2 * 148 * 3])
+@pytest.mark.parametrize("m", [3, 64, 128, 1000, 128 * 300 + 37, 128 * 2 * 148 * 3])
 def test_tc_minibatch_gradient(drl, m, mode):
     """tensor-core gradient (all-tf32 kernel; kernel with bf16 weight-gradient operands) vs float64 autograd of the oracle loss (and vs the fp32 CUDA-core kernel).
     Stated tolerance: every parameter block within 1e-2 of its own largest entry (tf32 operands carry
@@ -180,7 +180,7 @@ def test_tc_minibatch_gradient(drl, m, mode):
     np.testing.assert_allclose(st[0] / m, stats["policy_gradient_loss"], rtol=5e-3, atol=1e-4)
     np.testing.assert_allclose(st[1] / m, stats["value_loss"], rtol=5e-3)
     np.testing.assert_allclose(st[3] / m, stats["clip_fraction"], atol=2.0 / m)
-    assert 0.2 < stats["clip_fraction"] < 0.6
+    assert m < 128 or 0.2 < stats["clip_fraction"] < 0.6
     again = _grad(model, idx.to(torch.int32).cuda(), m, tc=mode)
     assert np.array_equal(g, again)                       # fixed tile order + fixed-order reduction
     model.close()
