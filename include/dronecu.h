@@ -133,7 +133,8 @@ void dronecu_config_vector(dronecu_config* cfg);
 /* DroneGymEnv() x n_envs / VectorizedDroneGymEnv(batch_size=n_envs): allocates the state on
  * `device` and performs the constructor's reset (drone.py:46, vectorized_drone.py:36), so a
  * fresh env has ep_num == 1.  Env i has global id env_offset + i; all randomness is keyed by
- * (seed, global id), so results do not depend on how envs are sharded over GPUs. */
+ * (seed, global id), so results do not depend on how envs are sharded over GPUs.
+ * 1 <= n_envs <= 2^30 per handle (80 bytes of state each; the kernels index envs with 32 bits). */
 int dronecu_create(const dronecu_config* cfg, int device, int64_t n_envs, int64_t env_offset,
                    uint64_t seed, dronecu_env** out);
 int dronecu_destroy(dronecu_env* env);
