@@ -46,7 +46,7 @@ constexpr int kTmem3 = 512;
 struct alignas(1024) Smem3 {
   unsigned char bufA[kWG3][9 * kGrp];    // bf16: groups 0..7 = H1, later dZ1; group 8 = G (g3[0..3] | live | 0 0 0)
   unsigned char bufB[kWG3][8 * kGrp];    // bf16: H2, later dZ2
-  unsigned char XN[kWG3][2 * kGrp];      // bf16: X (x0..x14, 1): B of S6
+  unsigned char XN[kWG3][2][2 * kGrp];   // bf16: X (x0..x14, 1): B of S6; double-buffered (tile parity) so that the next tile is staged while S6 runs
   unsigned char XG[kWG3][16384];         // tf32 X tile (A of S1, 9216 B), then bf16(1 - H1^2), 128 B per sample
   float W1[kHid * 16];
   float W2[kHid * kHid];
@@ -59,7 +59,8 @@ struct alignas(1024) Smem3 {
   float wsum[kWG3][4][kNS];
   alignas(8) unsigned long long full[kWG3];     // operands of S1 / S2 / S3 staged (served by issuer warp 0)
   alignas(8) unsigned long long fullA[kWG3];    // operands of S4 / S5 / S6 staged (served by issuer warp 1, fixed order)
-  alignas(8) unsigned long long done[kWG3];
+  alignas(8) unsigned long long done[kWG3];     // S1 / S2 / S3 completed (commit of issuer warp 0)
+  alignas(8) unsigned long long doneA[kWG3];    // S4 / S5 / S6 completed (commit of issuer warp 1)
   uint32_t tmem_base, pad1[3];
 };
 
@@ -113,7 +114,7 @@ __device__ __forceinline__ void setup3(Smem3& S, const float* __restrict__ theta
     S.log_std[tid] = theta[O_LOGSTD + tid];
   }
   if (tid == 0) {
-    for (int w = 0; w < kWG3; ++w) { mbar_init(&S.full[w], 128); mbar_init(&S.fullA[w], 128); mbar_init(&S.done[w], 1); }
+    for (int w = 0; w < kWG3; ++w) { mbar_init(&S.full[w], 128); mbar_init(&S.fullA[w], 128); mbar_init(&S.done[w], 1); mbar_init(&S.doneA[w], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
@@ -139,8 +140,8 @@ __device__ __forceinline__ void issuer3(Smem3& S, const int64_t n_tiles, const i
   const uint64_t dW1 = desc_w(smem_addr(S.W1), 16, 0), dW2 = desc_w(smem_addr(S.W2), kHid, 0), dW2T = desc_w(smem_addr(S.W2T), kHid, 0);
   const uint64_t dW3p = desc_w(smem_addr(S.W3p), kHid, 0), dW3k = desc_w(smem_addr(S.W3k), 8, 0);
   const uint64_t dXs0 = make_desc(smem_addr(S.XG[0]), kXsLbo, kXsSbo, 0);
-  const uint64_t dA0 = desc_il(smem_addr(S.bufA[0]), 0), dB0 = desc_il(smem_addr(S.bufB[0]), 0), dXn0 = desc_il(smem_addr(S.XN[0]), 0);
-  constexpr uint64_t kStrA = (9 * kGrp) >> 4, kStrB = (8 * kGrp) >> 4, kStrXn = (2 * kGrp) >> 4, kStrXs = 16384 >> 4, kOffG = (8 * kGrp) >> 4;
+  const uint64_t dA0 = desc_il(smem_addr(S.bufA[0]), 0), dB0 = desc_il(smem_addr(S.bufB[0]), 0), dXn0 = desc_il(smem_addr(S.XN[0][0]), 0);
+  constexpr uint64_t kStrA = (9 * kGrp) >> 4, kStrB = (8 * kGrp) >> 4, kStrXn = (4 * kGrp) >> 4, kParXn = (2 * kGrp) >> 4, kStrXs = 16384 >> 4, kOffG = (8 * kGrp) >> 4;
   const uint32_t tbase = S.tmem_base;
   constexpr uint64_t kW = 256 >> 4, kXs = (2 * kXsLbo) >> 4, kIl = 256 >> 4;      // per-slice bumps of the start-address field
   int steps_[kWG3];
@@ -155,6 +156,7 @@ __device__ __forceinline__ void issuer3(Smem3& S, const int64_t n_tiles, const i
   uint32_t ph_mask = 0;                                // bit w: parity of warpgroup w's `full` barrier
   uint32_t stp_pack = 0;                               // 4 bits per warpgroup: its next step (0..5)
   uint32_t seen3 = 0, seen2 = 0, seen1 = 0;            // has the shared accumulator been written yet
+  uint32_t xn_par = 0;                                 // bit w: which XN buffer warpgroup w's current tile uses
   int tix = 0;
   for (int v = 0; v < vmax; ++v) {
 #pragma unroll 1
@@ -198,14 +200,14 @@ __device__ __forceinline__ void issuer3(Smem3& S, const int64_t n_tiles, const i
 #pragma unroll
           for (int s = 0; s < 8; ++s) mma_bf16_ss(tbase + kAcc2, dZ + kIl * s, dHG + kIl * s, idesc_bf16(64, 72, 1, 1), seen2 | (s > 0));
         } else {                    // S6: dW1 | db1 += dZ1^T . [X | 1] (bf16, N = 16)
-          const uint64_t dZ = dA0 + kStrA * uw, dX = dXn0 + kStrXn * uw;
+          const uint64_t dZ = dA0 + kStrA * uw, dX = dXn0 + kStrXn * uw + kParXn * (uint64_t)((xn_par >> w) & 1u);
 #pragma unroll
           for (int s = 0; s < 8; ++s) mma_bf16_ss(tbase + kAcc1, dZ + kIl * s, dX + kIl * s, idesc_bf16(64, 16, 1, 1), seen1 | (s > 0));
         }
-        mma_commit(&S.done[w]);
+        mma_commit(ROLE ? &S.doneA[w] : &S.done[w]);
       }
       // the accumulate flags are warp-uniform state: every lane tracks them (only the elected lane issues)
-      if (step == 3) seen3 = 1; else if (step == 4) seen2 = 1; else if (step == 5) seen1 = 1;
+      if (step == 3) seen3 = 1; else if (step == 4) seen2 = 1; else if (step == 5) { seen1 = 1; xn_par ^= 1u << w; }
       __syncwarp();
       if (w == 0) TSTAMP(tlog, tix, 2 * step + 1);
     }
@@ -251,13 +253,15 @@ __global__ void __launch_bounds__(tcb::kThreads3, 1) ppo_grad_bf16_kernel(const 
 
     unsigned char* const rowA = S.bufA[wg] + r * 16;       // + g * kGrp: this sample's 16 bytes of feature group g
     unsigned char* const rowB = S.bufB[wg] + r * 16;
-    unsigned char* const XN = S.XN[wg];
+    unsigned char* const XN0 = S.XN[wg][0];
     unsigned char* const XS = S.XG[wg];
     unsigned char* const rowG1 = S.XG[wg] + r * 128;       // 8 chunks of 16 B, chunk c at ((c ^ (r & 7)) << 4)
     const int sw = r & 7;
     unsigned long long* const full = &S.full[wg];
     unsigned long long* const fullA = &S.fullA[wg];
     unsigned long long* const done = &S.done[wg];
+    unsigned long long* const doneA = &S.doneA[wg];
+    uint32_t phA = 0;
     const uint32_t tmem = S.tmem_base + wg * kWgCols;
     const uint32_t tL = tmem + ((uint32_t)(wq * 32) << 16);
     uint32_t ph = 0;
@@ -304,13 +308,16 @@ __global__ void __launch_bounds__(tcb::kThreads3, 1) ppo_grad_bf16_kernel(const 
       TSTAMP(tlog, it, 0);
       const float4 act = cur.act;
       const float old_logp = cur.old_logp, adv_raw = cur.adv_raw, ret = cur.ret;
-      if (it > 0) { mbar_wait(done, ph); ph ^= 1; fence_after(); }    // S6 of the previous tile has read bufA / XN
+      // The next tile is staged and handed over (S1) WITHOUT waiting for S6 of the previous one: X goes to the other XN
+      // buffer and to XS, neither of which S6 reads.  XS aliases this warp's rows of the tanh' stash: every lane of the
+      // warp has read its row (before handing S6 over) -- make that warp-wide.
+      __syncwarp();
       TSTAMP(tlog, it, 1);
       // ---------------- X -> shared memory: tf32 [samples x 16] (A of S1) and bf16 MN-major (B of S6) ----------------
       {
         const int col = lane & 15, half = lane >> 4, base = 32 * wq + half;
         const uint32_t live_mask = __ballot_sync(0xffffffffu, live) >> half;
-        unsigned char* const xn = XN + (col >> 3) * kGrp + (col & 7) * 2;
+        unsigned char* const xn = XN0 + (it & 1) * (2 * kGrp) + (col >> 3) * kGrp + (col & 7) * 2;
 #pragma unroll
         for (int p = 0; p < 16; ++p) {
           float v = (col < kObs) ? cur.xe[p] : 1.0f;
@@ -325,6 +332,7 @@ __global__ void __launch_bounds__(tcb::kThreads3, 1) ppo_grad_bf16_kernel(const 
       row_cur = row_nxt;
       row_nxt = row_of(tile + 2 * stride);
       TSTAMP(tlog, it, 3);
+      if (it > 0) { mbar_wait(doneA, phA); phA ^= 1; fence_after(); }    // S6 of the previous tile has read bufA (H1 goes there next)
 
       // ---------------- S1 done: H1 = tanh(D1) -> P (tf32, A of S2), bufA (bf16, B of S5), 1 - H1^2 -> stash ----------------
       mbar_wait(done, ph); ph ^= 1; fence_after();
@@ -445,7 +453,7 @@ __global__ void __launch_bounds__(tcb::kThreads3, 1) ppo_grad_bf16_kernel(const 
       TSTAMP(tlog, it, 9);
 
       // ---------------- S4 done: dZ2 = dH2 * (1 - H2^2) -> Q (tf32, A of S5), bufB (bf16, A of S5's wgrad) ----------------
-      mbar_wait(done, ph); ph ^= 1; fence_after();
+      mbar_wait(doneA, phA); phA ^= 1; fence_after();
       TSTAMP(tlog, it, 10);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -475,7 +483,7 @@ __global__ void __launch_bounds__(tcb::kThreads3, 1) ppo_grad_bf16_kernel(const 
         uint4 g1[8];                              // the stash does not depend on S5: read it while S5 runs
 #pragma unroll
         for (int c = 0; c < 8; ++c) g1[c] = *reinterpret_cast<const uint4*>(rowG1 + ((c ^ sw) << 4));
-        mbar_wait(done, ph); ph ^= 1; fence_after();
+        mbar_wait(doneA, phA); phA ^= 1; fence_after();
         TSTAMP(tlog, it, 12);
         float va[16], vb[16];
         ld16_issue(tL + kCP, va);
@@ -499,7 +507,7 @@ __global__ void __launch_bounds__(tcb::kThreads3, 1) ppo_grad_bf16_kernel(const 
       hand_over(fullA);                          // S6; awaited at the top of the next tile / after the loop
       TSTAMP(tlog, it, 13);
     }
-    if (it > 0) { mbar_wait(done, ph); ph ^= 1; }
+    if (it > 0) { mbar_wait(doneA, phA); phA ^= 1; }
     fence_after();
 
     // ---------------- per-thread scalars: warp sums, then fixed-order sums over warps and warpgroups ----------------
