@@ -497,7 +497,10 @@ def run_ppo(args):
     if rank == 0:
         line = {"metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "vs_baseline": None,
+                "dtype": ("f32" if args.precision == "fp32" else "tf32 (fp32 accumulate)") if wl == "c3" else
+                         "rollout MLP %s, update %s (fp32 accumulate; env step, loss, Adam in f32)" % (args.precision, args.update_precision or args.precision),
+                "data": "synthetic",
                 "config": {"workload": WORKLOAD_NAMES[wl], "envs_per_gpu": n, "n_steps": K, "n_epochs": args.ppo_epochs,
                            "minibatches_per_epoch": args.ppo_minibatches, "policy": "MlpPolicy 15-64-64-{4,1} tanh, random init", "rollout_precision": args.precision,
                            "update_precision": args.update_precision or args.precision,
