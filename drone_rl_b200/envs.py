@@ -278,3 +278,62 @@ class DroneVecEnv(_HostEnvBase):
 
     def episode_stats(self, reset=False):
         return self.batch.episode_stats(reset)
+
+
+def make_sb3_vec_env(n_envs: int = 1, **kwargs):
+    """A real ``stable_baselines3.common.vec_env.VecEnv`` over ``DroneVecEnv`` -- what the reference's
+    ``VecMonitor(DummyVecEnv([DroneGymEnv] * n))`` (train.py:18-20, :33-35) becomes when stable-baselines3 is installed
+    next to this package: ``PPO("MlpPolicy", env=make_sb3_vec_env(n), device="cpu")`` then runs the stock SB3 algorithm
+    on the CUDA env (SB3 insists on ``isinstance(env, VecEnv)``, and on gymnasium spaces).
+
+    SB3 is NOT in this image: the subclass is built lazily here and exercised in the tests against
+    stub modules with SB3's published abstract interface (reset / step_async / step_wait / close / get_attr / set_attr /
+    env_method / env_is_wrapped; ``VecEnv.__init__(num_envs, observation_space, action_space)``) -- UNPINNED like every
+    SB3-facing piece.  Raises ImportError when stable-baselines3 or gymnasium is missing.
+    """
+    from stable_baselines3.common.vec_env import VecEnv          # noqa: the optional dependency
+    import gymnasium
+
+    inner = DroneVecEnv(n_envs, info_mode="sb3", copy=True, **kwargs)
+    obs_space = gymnasium.spaces.Box(low=-np.inf, high=np.inf, shape=inner.observation_space.shape, dtype=np.float32)
+    act_space = gymnasium.spaces.Box(low=0.0, high=float(inner.batch.config.motor_max), shape=(4,), dtype=np.float32)
+
+    class DroneSB3VecEnv(VecEnv):
+        def __init__(self):
+            super().__init__(inner.num_envs, obs_space, act_space)
+            self.inner, self.batch = inner, inner.batch
+
+        def reset(self):
+            return inner.reset()
+
+        def step_async(self, actions):
+            inner.step_async(np.asarray(actions, dtype=np.float32))
+
+        def step_wait(self):
+            return inner.step_wait()
+
+        def close(self):
+            inner.close()
+
+        def get_attr(self, attr_name, indices=None):
+            return inner.get_attr(attr_name, indices)
+
+        def set_attr(self, attr_name, value, indices=None):
+            inner.set_attr(attr_name, value, indices)
+
+        def env_method(self, method_name, *method_args, indices=None, **method_kwargs):
+            return inner.env_method(method_name, *method_args, indices=indices, **method_kwargs)
+
+        def env_is_wrapped(self, wrapper_class, indices=None):
+            return inner.env_is_wrapped(wrapper_class, indices)
+
+        def seed(self, seed=None):
+            return inner.seed(seed)
+
+        def get_images(self):
+            return [None] * inner.num_envs
+
+        def episode_stats(self, reset=False):
+            return inner.episode_stats(reset)
+
+    return DroneSB3VecEnv()

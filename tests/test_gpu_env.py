@@ -474,3 +474,66 @@ def test_euler_angle_range_of_sincos(drl, scale):
     worst = _assert_close(got, ref, amp, f"state at |angle| <= {scale:g}")
     _assert_close(res["reward"], orc["reward"], 1.0, "reward")
     print(f"scale {scale:g}: worst err/bound = {worst:.3f}")
+
+
+def test_sb3_vecenv_adapter_against_stub_interface(drl, monkeypatch):
+    """make_sb3_vec_env builds a genuine subclass of SB3's abstract VecEnv.  stable-baselines3 / gymnasium are not in this
+    image, so the abstract interface (SB3's published one) is stubbed: every abstract method must be implemented, the
+    constructor arguments are (num_envs, observation_space, action_space), and the step protocol returns SB3's types."""
+    import abc
+    import sys
+    import types
+    from drone_rl_b200 import envs
+
+    class VecEnv(abc.ABC):
+        def __init__(self, num_envs, observation_space, action_space):
+            self.num_envs, self.observation_space, self.action_space = num_envs, observation_space, action_space
+
+        @abc.abstractmethod
+        def reset(self): ...
+        @abc.abstractmethod
+        def step_async(self, actions): ...
+        @abc.abstractmethod
+        def step_wait(self): ...
+        @abc.abstractmethod
+        def close(self): ...
+        @abc.abstractmethod
+        def get_attr(self, attr_name, indices=None): ...
+        @abc.abstractmethod
+        def set_attr(self, attr_name, value, indices=None): ...
+        @abc.abstractmethod
+        def env_method(self, method_name, *method_args, indices=None, **method_kwargs): ...
+        @abc.abstractmethod
+        def env_is_wrapped(self, wrapper_class, indices=None): ...
+
+        def step(self, actions):
+            self.step_async(actions)
+            return self.step_wait()
+
+    class Box:
+        def __init__(self, low, high, shape, dtype):
+            self.low, self.high, self.shape, self.dtype = low, high, shape, dtype
+
+    sb3, common, vec = types.ModuleType("stable_baselines3"), types.ModuleType("stable_baselines3.common"), types.ModuleType("stable_baselines3.common.vec_env")
+    vec.VecEnv = VecEnv
+    gymn, spaces = types.ModuleType("gymnasium"), types.ModuleType("gymnasium.spaces")
+    spaces.Box = Box
+    gymn.spaces = spaces
+    for name, mod in (("stable_baselines3", sb3), ("stable_baselines3.common", common), ("stable_baselines3.common.vec_env", vec),
+                      ("gymnasium", gymn), ("gymnasium.spaces", spaces)):
+        monkeypatch.setitem(sys.modules, name, mod)
+    env = envs.make_sb3_vec_env(64, seed=3)
+    assert isinstance(env, VecEnv) and env.num_envs == 64
+    assert env.observation_space.shape == (15,) and env.action_space.shape == (4,) and abs(env.action_space.high - 7.3575) < 1e-6
+    obs = env.reset()
+    assert obs.shape == (64, 15) and obs.dtype == np.float32
+    seen = 0
+    for _ in range(80):
+        obs, rew, done, infos = env.step(np.random.default_rng(0).uniform(0, 7.3575, (64, 4)))   # float64 in, like SB3's clipped actions
+        assert rew.dtype == np.float32 and done.dtype == np.bool_ and isinstance(infos, list) and len(infos) == 64
+        for i in np.flatnonzero(done):
+            assert infos[i]["terminal_observation"].shape == (15,) and {"r", "l", "t"} <= set(infos[i]["episode"])
+            seen += 1
+    assert seen > 0
+    assert len(env.get_attr("pos")) == 64 and env.env_is_wrapped(object) == [False] * 64
+    env.close()
