@@ -5,8 +5,8 @@ Same flow as the reference script:
     learning_rate=3e-4)``, train.py:11-31), else a fresh ``PPO("MlpPolicy")`` with SB3's defaults (train.py:33-43);
   * a numbered run directory ``./tensorboard/drone_runs_<n>`` (helper.py:6-21 ``make_run_dir``);
   * scalars under SB3's key names (``rollout/ep_rew_mean``, ``train/value_loss`` ...) to stdout and to
-    ``progress.csv`` / ``progress.jsonl`` in the run dir (a TensorBoard event file as well when the
-    ``tensorboard`` package is importable; it is not in this image);
+    ``progress.csv`` / ``progress.jsonl`` and a TensorBoard event file (``events.out.tfevents.*``, written by
+    ``tb_events.py`` -- the ``tensorboard`` package itself is not needed) in the run dir;
   * the trajectory callback (traj_tb.py:31-73): every ``record_interval``-th finished episode of env 0 is
     buffered and every ``block_size`` episodes the overlays XY / XZ / YZ are written -- here from the rollout
     buffer itself (``obs[:, 0, 0:3]`` is the position before each step: ONE device->host copy per rollout instead
@@ -40,18 +40,14 @@ def make_run_dir(root_dir: str, prefix: str = "drone_runs_") -> str:
 
 
 class RunLogger:
-    """stdout table + progress.csv + progress.jsonl (+ TensorBoard scalars when available), SB3 key names."""
+    """stdout table + progress.csv + progress.jsonl + TensorBoard event file, SB3 key names."""
 
     def __init__(self, run_dir: str, stdout: bool = True):
         self.run_dir, self.stdout, self.rows, self.keys = run_dir, stdout, 0, None
         self.jsonl = open(os.path.join(run_dir, "progress.jsonl"), "w")
         self.csv_path = os.path.join(run_dir, "progress.csv")
-        self.tb = None
-        try:                                             # pragma: no cover - tensorboard is not in this image
-            from torch.utils.tensorboard import SummaryWriter
-            self.tb = SummaryWriter(run_dir)
-        except Exception:
-            self.tb = None
+        from .tb_events import EventFileWriter
+        self.tb = EventFileWriter(run_dir)               # TensorBoard scalars (own writer: the package is not needed)
 
     def dump(self, values: dict, step: int):
         self.jsonl.write(json.dumps({"step": step, **values}) + "\n")
@@ -62,10 +58,7 @@ class RunLogger:
                 csv.writer(f).writerow(["step"] + self.keys)
         with open(self.csv_path, "a", newline="") as f:
             csv.writer(f).writerow([step] + [values.get(k, "") for k in self.keys])
-        if self.tb is not None:                          # pragma: no cover
-            for k, v in values.items():
-                if isinstance(v, (int, float)):
-                    self.tb.add_scalar(k, v, step)
+        self.tb.add_scalars(values, step)
         if self.stdout:
             groups: dict = {}
             for k, v in values.items():
@@ -83,8 +76,7 @@ class RunLogger:
 
     def close(self):
         self.jsonl.close()
-        if self.tb is not None:                          # pragma: no cover
-            self.tb.close()
+        self.tb.close()
 
 
 class TrajectoryCallback:

@@ -129,3 +129,25 @@ def test_sb3_zip_import_and_export_round_trip(tmp_path):
     mean, value, _ = po.forward(params, x)
     assert torch.allclose(pol.action_net(pol.mlp_extractor.policy_net(x)), mean, atol=1e-6)
     assert torch.allclose(pol.value_net(pol.mlp_extractor.value_net(x)).squeeze(-1), value, atol=1e-6)
+
+
+def test_tensorboard_event_file_format(tmp_path):
+    """The scalar event file: CRC-32C known answer, TFRecord framing, Event / Summary protobuf subset round trip."""
+    import glob
+    import struct
+    from drone_rl_b200 import tb_events as tb
+    assert tb.crc32c(b"123456789") == 0xE3069283                      # the CRC-32C check value
+    assert tb.crc32c(b"") == 0 and tb.crc32c(bytes(32)) == 0x8A9136AA  # RFC 3720 B.4: 32 bytes of zeros
+    lg = RunLogger(str(tmp_path), stdout=False)
+    lg.dump({"rollout/ep_rew_mean": -1.5, "train/value_loss": 0.25, "time/iterations": 1, "note": "skipped"}, 2048)
+    lg.dump({"rollout/ep_rew_mean": -1.25, "train/value_loss": 0.125, "time/iterations": 2}, 300000)
+    lg.close()
+    (path,) = glob.glob(str(tmp_path / "events.out.tfevents.*"))
+    raw = open(path, "rb").read()
+    (n0,) = struct.unpack("<Q", raw[:8])
+    assert raw[12:12 + n0].endswith(b"brain.Event:2")                 # first record: the file-version event
+    ev = tb.read_events(path)
+    assert ev[0]["file_version"] == "brain.Event:2" and len(ev) == 3
+    assert ev[1]["step"] == 2048 and ev[2]["step"] == 300000
+    assert ev[1]["scalars"] == {"rollout/ep_rew_mean": -1.5, "train/value_loss": 0.25, "time/iterations": 1.0}
+    assert ev[2]["scalars"]["train/value_loss"] == 0.125
