@@ -112,8 +112,31 @@ class DroneGymEnv(_HostEnvBase):
         return np.concatenate([s["pos"][0], s["vel"][0], s["euler"][0], s["omega"][0],
                                s["target"][0] - s["pos"][0]]).astype(np.float32)
 
+    # rendering / recording (drone.py:189-248; test.py:10-22) -- Pillow instead of matplotlib, see render.py ---------------
+    def start_record(self, filename="drone_run.gif", dpi=200, fps=20, bitrate=-1):
+        """Call before the loop; every ``render()`` then grabs a frame (drone.py:189-197).  ``dpi`` / ``bitrate`` are
+        accepted for signature compatibility; the output is an animated GIF (what the reference's PillowWriter writes)."""
+        from .render import Recorder
+        self._recorder = Recorder(filename, fps=fps)
+
+    def stop_record(self):
+        """Finish and save the recording (drone.py:199-203)."""
+        rec = getattr(self, "_recorder", None)
+        if rec is not None:
+            rec.finish()
+            self._recorder = None
+
     def render(self, mode="human", close=False):
-        raise NotImplementedError("rendering (drone.py:205-248) is host-side matplotlib, out of scope (SURVEY.md section 2)")
+        """Draw the scene of drone.py:205-241 (target, arms, centre, motors in the [-5,5] x [-5,5] x [0,5] box); returns the
+        PIL image, and appends it to the recording when one is active (drone.py:243-248).  There is no live window."""
+        from .render import FrameRenderer
+        if getattr(self, "_renderer", None) is None:
+            self._renderer = FrameRenderer()
+        s = self.batch.get_state("pos", "euler", "target")
+        img = self._renderer.draw(s["pos"][0], s["euler"][0], s["target"][0], self.arm_length)
+        if getattr(self, "_recorder", None) is not None:
+            self._recorder.grab(img)
+        return img
 
     def close(self):
         self.batch.close()

@@ -50,3 +50,21 @@ def test_train_driver_many_envs_and_trajectory_blocks(tmp_path, monkeypatch):
     assert "ep_2" in z.files and z["ep_2"].shape[1] == 3 and z["ep_2"].shape[0] >= 2
     assert abs(float(z["ep_2"][0, 2]) - 1.0) < 1e-6                       # episodes start at z = 1 (drone.py:57)
     assert os.path.isfile("ppo_drone_rel_obs_pos_reward.zip")            # train.py:70
+
+
+def test_eval_script_records_a_gif(tmp_path, monkeypatch):
+    """The reference's test.py flow: PPO.load('./dd.zip'), 100 deterministic steps in a DroneGymEnv with start_record /
+    render / stop_record -> an animated GIF with one frame per step."""
+    from PIL import Image
+    from drone_rl_b200 import test as eval_script
+    from drone_rl_b200 import train
+    monkeypatch.chdir(tmp_path)
+    train.main(["--total-timesteps", "2048", "--quiet", "--save", "dd"])
+    eval_script.main(["--steps", "30"])
+    g = Image.open("my_drone_run.gif")
+    # Pillow merges identical consecutive frames (adding their durations): count the time, not the frames
+    total = 0
+    for k in range(g.n_frames):
+        g.seek(k)
+        total += g.info["duration"]
+    assert g.is_animated and 20 <= g.n_frames <= 30 and total == 30 * 50 and g.size == (480, 480)

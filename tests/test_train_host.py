@@ -151,3 +151,31 @@ def test_tensorboard_event_file_format(tmp_path):
     assert ev[1]["step"] == 2048 and ev[2]["step"] == 300000
     assert ev[1]["scalars"] == {"rollout/ep_rew_mean": -1.5, "train/value_loss": 0.25, "time/iterations": 1.0}
     assert ev[2]["scalars"]["train/value_loss"] == 0.125
+
+
+def test_pillow_renderer_scene_and_gif(tmp_path):
+    """render.py: the reference's scene (drone.py:205-241) drawn with Pillow -- target green, arms purple, centre red,
+    motors blue -- and a recording saved as an animated GIF; geometry of the motors as drone.py:222-229."""
+    from PIL import Image
+    from drone_rl_b200 import render
+    m = render.motor_positions([1.0, 2.0, 3.0], [0.0, 0.0, 0.0], 0.5)
+    a = 0.5 / np.sqrt(2)
+    assert np.allclose(m, [[1 + a, 2 + a, 3], [1 - a, 2 + a, 3], [1 - a, 2 - a, 3], [1 + a, 2 - a, 3]])
+    R = render.rotation_matrix([0.3, -0.2, 1.1])
+    assert np.allclose(R @ R.T, np.eye(3), atol=1e-12) and abs(np.linalg.det(R) - 1) < 1e-12
+    assert np.allclose(R[:, 2], [np.cos(1.1) * np.sin(-0.2) * np.cos(0.3) + np.sin(1.1) * np.sin(0.3),
+                                 np.sin(1.1) * np.sin(-0.2) * np.cos(0.3) - np.cos(1.1) * np.sin(0.3),
+                                 np.cos(-0.2) * np.cos(0.3)])                       # the column the dynamics use (drone.py:170-172)
+    fr = render.FrameRenderer(size=240)
+    img = fr.draw([0.0, 0.0, 2.0], [0.1, 0.2, 0.3], [1.0, -1.0, 3.0], 2.0)          # long arms: visible between the dots
+    px = np.asarray(img).reshape(-1, 3)
+    has = lambda c: bool((px == np.array(c)).all(1).any())
+    assert has((0, 160, 0)) and has((128, 0, 128)) and has((220, 0, 0)) and has((0, 0, 220))
+    img_nan = fr.draw([np.nan, 0, 0], [0, 0, 0], [0, 0, 1], 0.5)                    # a diverged env still renders the box + target
+    assert bool((np.asarray(img_nan).reshape(-1, 3) == np.array((0, 160, 0))).all(1).any())
+    rec = render.Recorder(str(tmp_path / "run.mp4"), fps=20)                        # the reference's default name ends in .mp4
+    for k in range(5):
+        rec.grab(fr.draw([0.0, 0.0, 1.0 + 0.2 * k], [0, 0, 0.1 * k], [0, 0, 3.0], 0.5))
+    rec.finish()
+    g = Image.open(tmp_path / "run.gif")
+    assert g.is_animated and g.n_frames == 5 and g.info["duration"] == 50
