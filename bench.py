@@ -52,6 +52,22 @@ def peaks():
 # ------------------------------------------------------------------------------------------------
 # clocks sampler (pynvml) -- runs during the timed region
 # ------------------------------------------------------------------------------------------------
+class stdout_to_stderr:
+    """NCCL (and torch's process group) print a version banner on STDOUT when the communicator is created; the contract is ONE
+    JSON line on stdout, so file descriptor 1 points at stderr while the process group initialises and runs its first collective."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self._saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *a):
+        sys.stdout.flush()
+        os.dup2(self._saved, 1)
+        os.close(self._saved)
+
+
 class ClockSampler:
     REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
                0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
@@ -262,7 +278,10 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        with stdout_to_stderr():
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()                           # creates the communicator (and prints NCCL's banner) now
+            torch.cuda.synchronize()
     import drone_rl_b200 as drl
 
     wl = args.workload
@@ -402,7 +421,10 @@ def run_ppo(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        with stdout_to_stderr():
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
     import drone_rl_b200 as drl
     from drone_rl_b200.ppo import PPO
     wl = args.workload
