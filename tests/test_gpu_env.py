@@ -446,10 +446,10 @@ def test_chunked_host_step_equals_device_step(drl):
     venv.close(); ref.close()
 
 
-@pytest.mark.parametrize("scale", [1.0, 50.0, 3e3, 1.0e5, 1.056e5, 1.0e7])
+@pytest.mark.parametrize("scale", [1.0, 50.0, 3e3, 1.0e5, 1.056e5, 1.0e7, 5.0e8, 1.05e9, 3.0e9, 1.0e15])
 def test_euler_angle_range_of_sincos(drl, scale):
-    """The kernel's own sin/cos of the three Euler angles (one range check, Cody-Waite by pi/2 below 105615 rad,
-    libm above) against the float64 oracle, teacher-forced, for angles from +-1 rad up to +-1e7 rad -- the reference
+    """The kernel's own sin/cos of the three Euler angles (float Cody-Waite by pi/2 below 105615 rad, float64 Cody-Waite
+    up to 2^30, libm above) against the float64 oracle, teacher-forced, for angles from +-1 rad up to +-1e7 rad -- the reference
     never wraps its angles (drone.py:131), so every magnitude a long episode can reach must stay within 1e-5
     relative.  Mixed rows (one angle above the fast-path limit, two below) exercise the shared range check."""
     rng = np.random.default_rng(int(scale) % 9973)
