@@ -197,7 +197,12 @@ class VectorizedDroneGymEnv(_HostEnvBase):
         return np.concatenate([s["pos"], s["vel"], s["euler"], s["omega"]], axis=1).astype(np.float32)
 
     def render(self, ax=None):
-        raise NotImplementedError("rendering (vectorized_drone.py:218-243) is host-side matplotlib, out of scope")
+        """The scene of vectorized_drone.py:218-243 (target + every drone centre in the [-20,20] x [-20,20] x [0,20] box) as a
+        PIL image (render.py); `ax` (a matplotlib axis in the reference) is ignored, there is no live window."""
+        from .render import FrameRenderer
+        if getattr(self, "_renderer", None) is None:
+            self._renderer = FrameRenderer(xlim=(-20.0, 20.0), ylim=(-20.0, 20.0), zlim=(0.0, 20.0))
+        return self._renderer.draw_batch(self._attr("pos"), self.target)
 
     def close(self):
         self.batch.close()

@@ -74,6 +74,26 @@ class FrameRenderer:
         return img
 
 
+    def draw_batch(self, pos, target):
+        """vectorized_drone.py:218-243: the target (green) and every drone centre (red) -- use limits (-20, 20), (-20, 20), (0, 20)."""
+        from PIL import Image, ImageDraw
+        img = Image.new("RGB", (self.size, self.size), "white")
+        d = ImageDraw.Draw(img)
+        (x0, x1), (y0, y1), (z0, z1) = self.lim
+        floor = [(x0, y0, z0), (x1, y0, z0), (x1, y1, z0), (x0, y1, z0)]
+        for a, b in zip(floor, floor[1:] + floor[:1]):
+            d.line([self.project(a), self.project(b)], fill=(170, 170, 170), width=1)
+        for c in floor:
+            d.line([self.project(c), self.project((c[0], c[1], z1))], fill=(210, 210, 210), width=1)
+        u, v = self.project(target)
+        d.ellipse([u - 6, v - 6, u + 6, v + 6], fill=(0, 160, 0))
+        pos = np.asarray(pos, dtype=np.float64)
+        for p in pos[np.all(np.isfinite(pos), axis=1)]:
+            u, v = self.project(p)
+            d.ellipse([u - 3, v - 3, u + 3, v + 3], fill=(220, 0, 0))
+        return img
+
+
 class Recorder:
     """``start_record`` / ``stop_record`` state: frames of ``render()`` calls, saved as an animated GIF."""
 

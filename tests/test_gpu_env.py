@@ -537,3 +537,24 @@ def test_sb3_vecenv_adapter_against_stub_interface(drl, monkeypatch):
     assert seen > 0
     assert len(env.get_attr("pos")) == 64 and env.env_is_wrapped(object) == [False] * 64
     env.close()
+
+
+def test_render_returns_the_reference_scenes(drl):
+    """DroneGymEnv.render / VectorizedDroneGymEnv.render (drone.py:205-248, vectorized_drone.py:218-243): Pillow images of the
+    reference's scenes; recording collects one frame per render call."""
+    env = drl.DroneGymEnv(seed=1)
+    env.reset()
+    env.start_record("unused.gif", fps=10)
+    for _ in range(3):
+        env.step(np.full(4, 2.5, np.float32))
+        img = env.render()
+    assert img.size == (480, 480) and len(env._recorder.frames) == 3
+    px = np.asarray(img).reshape(-1, 3)
+    assert bool((px == np.array((220, 0, 0))).all(1).any())           # the drone centre
+    env._recorder = None                                              # do not write a file from the test
+    env.close()
+    venv = drl.VectorizedDroneGymEnv(batch_size=7)
+    venv.reset()
+    imgb = np.asarray(venv.render()).reshape(-1, 3)
+    assert bool((imgb == np.array((0, 160, 0))).all(1).any()) and bool((imgb == np.array((220, 0, 0))).all(1).any())
+    venv.close()

@@ -173,6 +173,9 @@ def test_pillow_renderer_scene_and_gif(tmp_path):
     assert has((0, 160, 0)) and has((128, 0, 128)) and has((220, 0, 0)) and has((0, 0, 220))
     img_nan = fr.draw([np.nan, 0, 0], [0, 0, 0], [0, 0, 1], 0.5)                    # a diverged env still renders the box + target
     assert bool((np.asarray(img_nan).reshape(-1, 3) == np.array((0, 160, 0))).all(1).any())
+    fb = render.FrameRenderer(size=240, xlim=(-20, 20), ylim=(-20, 20), zlim=(0, 20))
+    imgb = np.asarray(fb.draw_batch(np.array([[0, 0, 1.0], [3, -2, 5.0], [np.nan, 0, 0]]), [0, 0, 10.0])).reshape(-1, 3)
+    assert bool((imgb == np.array((0, 160, 0))).all(1).any()) and bool((imgb == np.array((220, 0, 0))).all(1).any())
     rec = render.Recorder(str(tmp_path / "run.mp4"), fps=20)                        # the reference's default name ends in .mp4
     for k in range(5):
         rec.grab(fr.draw([0.0, 0.0, 1.0 + 0.2 * k], [0, 0, 0.1 * k], [0, 0, 3.0], 0.5))
