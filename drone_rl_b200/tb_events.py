@@ -6,7 +6,8 @@ reference logs through SB3's ``configure(tb_log_dir, ["stdout", "tensorboard"])`
   TFRecord  = uint64 length | uint32 masked_crc32c(length) | bytes data | uint32 masked_crc32c(data)     (little endian)
   data      = serialized ``tensorflow.Event`` protobuf: 1 wall_time (double) | 2 step (int64) |
               3 file_version (string, first record: "brain.Event:2") | 5 summary (message)
-  Summary   = repeated 1 value { 1 tag (string) | 2 simple_value (float) }
+  Summary   = repeated 1 value { 1 tag (string) | 2 simple_value (float) | 4 image { 1 height | 2 width | 3 colorspace |
+              4 encoded_image_string (PNG bytes) } }
 
 ``read_events`` parses the same subset back (used by the tests; CRCs verified).
 """
@@ -55,6 +56,12 @@ def _field_bytes(num: int, payload: bytes) -> bytes:
     return _varint((num << 3) | 2) + _varint(len(payload)) + payload
 
 
+def _image_event(wall_time: float, step: int, tag: str, png: bytes, height: int, width: int) -> bytes:
+    image = b"\x08" + _varint(height) + b"\x10" + _varint(width) + b"\x18" + _varint(3) + _field_bytes(4, png)
+    value = _field_bytes(1, tag.encode()) + _field_bytes(4, image)
+    return b"\x09" + struct.pack("<d", wall_time) + b"\x10" + _varint(step) + _field_bytes(5, _field_bytes(1, value))
+
+
 def _event(wall_time: float, step: int = 0, file_version: str | None = None, scalars: dict | None = None) -> bytes:
     ev = b"\x09" + struct.pack("<d", wall_time) + b"\x10" + _varint(step)
     if file_version is not None:
@@ -84,6 +91,14 @@ class EventFileWriter:
         if nums:
             self._record(_event(time.time(), int(step), scalars=nums))
             self._f.flush()
+
+    def add_image(self, tag: str, pil_image, step: int):
+        """What SB3's ``writer.add_figure(tag, fig, step)`` stores (traj_tb.py:66): a PNG under an image summary."""
+        import io
+        b = io.BytesIO()
+        pil_image.convert("RGB").save(b, format="PNG")
+        self._record(_image_event(time.time(), int(step), tag, b.getvalue(), pil_image.height, pil_image.width))
+        self._f.flush()
 
     def close(self):
         self._f.close()
@@ -137,6 +152,10 @@ def read_events(path: str) -> list:
         for summary in f.get(5, []):
             for value in _parse(summary).get(1, []):
                 v = _parse(value)
-                ev["scalars"][v[1][0].decode()] = struct.unpack("<f", v[2][0])[0]
+                if 2 in v:
+                    ev["scalars"][v[1][0].decode()] = struct.unpack("<f", v[2][0])[0]
+                if 4 in v:
+                    im = _parse(v[4][0])
+                    ev.setdefault("images", {})[v[1][0].decode()] = {"height": im[1][0], "width": im[2][0], "png": im[4][0]}
         events.append(ev)
     return events

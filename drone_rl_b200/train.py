@@ -82,8 +82,9 @@ class RunLogger:
 class TrajectoryCallback:
     """traj_tb.py:7-73 restated over the rollout buffer: positions of env 0, episode by episode."""
 
-    def __init__(self, run_dir: str, record_interval: int = 25, block_size: int = 500, env_index: int = 0):
+    def __init__(self, run_dir: str, record_interval: int = 25, block_size: int = 500, env_index: int = 0, tb=None):
         self.run_dir, self.record_interval, self.block_size, self.env_index = run_dir, record_interval, block_size, env_index
+        self.tb = tb                           # EventFileWriter: the overlays also go to TensorBoard, as traj_tb.py:66 does
         self.positions: list = []
         self.episode_count = 0
         self.buffered: list = []
@@ -126,6 +127,9 @@ class TrajectoryCallback:
                     if len(xs) > 1:
                         d.line(list(zip(xs.tolist(), ys.tolist())), fill=col, width=1)
             img.save(base + ".png")
+            if self.tb is not None:
+                for p, tag in enumerate(("Overlay_XY", "Overlay_XZ", "Overlay_YZ")):
+                    self.tb.add_image(f"Trajectory/{tag}_block{block}", img.crop((p * size, 0, (p + 1) * size, size)), step)
         except Exception:                                   # Pillow missing: the .npz is the record
             pass
         self.buffered = []
@@ -185,7 +189,7 @@ def main(argv=None):
     if rank == 0:
         run_dir = make_run_dir(args.tensorboard_root, prefix="drone_runs_")
         logger = RunLogger(run_dir, stdout=not args.quiet)
-        cb = TrajectoryCallback(run_dir)
+        cb = TrajectoryCallback(run_dir, tb=logger.tb)
 
     def on_iteration(m):
         if rank == 0:

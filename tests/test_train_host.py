@@ -54,7 +54,9 @@ def test_trajectory_callback_segments_episodes(tmp_path):
     pos = np.arange(K * 3, dtype=np.float32).reshape(K, 3)
     done = np.zeros(K, bool)
     done[[9, 19, 29, 39, 49, 59]] = True                     # six episodes of ten steps
-    cb = TrajectoryCallback(str(tmp_path), record_interval=2, block_size=4)
+    from drone_rl_b200.tb_events import EventFileWriter, read_events
+    tbw = EventFileWriter(str(tmp_path))
+    cb = TrajectoryCallback(str(tmp_path), record_interval=2, block_size=4, tb=tbw)
     assert cb(_FakeModel(pos[:25], done[:25])) is True       # rollouts may cut an episode in two
     assert cb(_FakeModel(pos[25:], done[25:])) is True
     assert cb.episode_count == 6 and cb.blocks_written == 1
@@ -63,6 +65,13 @@ def test_trajectory_callback_segments_episodes(tmp_path):
     assert np.array_equal(z["ep_2"], pos[10:20]) and np.array_equal(z["ep_4"], pos[30:40])
     assert len(cb.buffered) == 1 and np.array_equal(cb.buffered[0], pos[50:60])   # episode 6, next block
     assert os.path.isfile(tmp_path / "trajectory_block1.png")
+    tbw.close()
+    imgs = {}
+    for ev in read_events(tbw.path):
+        imgs.update(ev.get("images", {}))
+    assert set(imgs) == {"Trajectory/Overlay_XY_block1", "Trajectory/Overlay_XZ_block1", "Trajectory/Overlay_YZ_block1"}   # traj_tb.py:50-66
+    one = imgs["Trajectory/Overlay_XY_block1"]
+    assert one["height"] == 360 and one["width"] == 360 and one["png"][:8] == b"\x89PNG\r\n\x1a\n"
 
 
 def _sb3_like_archive(path, params, m, v, step):
