@@ -68,6 +68,8 @@ class PPOConfig(C.Structure):
 
 POLICY_PARAMS = 10697
 GRAD_LEN = POLICY_PARAMS + 8
+IPC_HANDLE_BYTES = 64
+DP_MAX_WORLD = 16
 
 
 class Stats(C.Structure):
@@ -120,6 +122,14 @@ _SIGNATURES = {
     "dronecu_ppo_num_updates": (C.c_int64, [_P]),
     "dronecu_ppo_get_state": (C.c_int, [_P, _P, C.POINTER(C.c_int64), _P]),
     "dronecu_ppo_set_state": (C.c_int, [_P, _P, C.c_int64, _P]),
+    "dronecu_ppo_set_info_accumulator": (C.c_int, [_P, _P]),
+    # data-parallel exchange over peer memory
+    "dronecu_ppo_dp_alloc": (C.c_int, [_P, C.c_int, C.c_int, _P, C.POINTER(_P)]),
+    "dronecu_ppo_dp_connect": (C.c_int, [_P, C.c_int, _P, C.POINTER(_P)]),
+    "dronecu_ppo_dp_set_timeout": (C.c_int, [_P, C.c_double]),
+    "dronecu_ppo_dp_status": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int64)]),
+    "dronecu_ppo_dp_allreduce_f64": (C.c_int, [_P, _P, C.c_int, _P]),
+    "dronecu_ppo_apply_dp": (C.c_int, [_P, _P, _P, _P, _P]),
 }
 
 _lib = None

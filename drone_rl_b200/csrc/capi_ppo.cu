@@ -14,6 +14,7 @@
 #include "ppo_rollout_tc.cuh"
 #include "ppo_update_tc.cuh"
 #include "ppo_update_tc3.cuh"
+#include "ppo_dp.cuh"
 
 using namespace dronecu;
 
@@ -30,6 +31,11 @@ struct dronecu_ppo {
   long long* d_step; // device-resident Adam step count (ppo_apply_kernel increments it)
   uint64_t launches;
   float* dbg;        // see dronecu_ppo_debug_buffer
+  float* info_sum;   // see dronecu_ppo_set_info_accumulator (caller-owned, nullable)
+  // data-parallel exchange over peer memory (ppo_dp.cuh)
+  DpArgs dp;         // dp.world == 0: not set up
+  float* dp_mail;    // this rank's mailbox (cudaMalloc: exportable with cudaIpcGetMemHandle)
+  bool dp_opened[kDpMaxWorld];   // mail[r] was mapped with cudaIpcOpenMemHandle (to be closed)
 };
 
 static int rollout_policy_impl(dronecu_env* e, int K, const float* d_params, int deterministic,
@@ -159,6 +165,9 @@ extern "C" int dronecu_ppo_destroy(dronecu_ppo* p) {
   if (!p) return DRONECU_OK;
   DeviceGuard guard(p->device);
   cudaDeviceSynchronize();
+  for (int r = 0; r < kDpMaxWorld; ++r)
+    if (p->dp_opened[r]) cudaIpcCloseMemHandle(p->dp.mail[r]);
+  cudaFree(p->dp_mail); cudaFree(p->dp.seq); cudaFree(p->dp.status);
   cudaFree(p->partials); cudaFree(p->moments); cudaFree(p->adv_partials); cudaFree(p->d_step);
   cudaGetLastError();
   delete p;
@@ -314,7 +323,7 @@ extern "C" int dronecu_ppo_apply(dronecu_ppo* p, float* d_params, const float* d
   a.lr = p->cfg.learning_rate;
   a.step = p->d_step;
   a.beta1 = p->cfg.beta1; a.beta2 = p->cfg.beta2; a.eps = p->cfg.adam_eps; a.max_norm = p->cfg.max_grad_norm;
-  a.info = d_info;
+  a.info = d_info; a.info_sum = p->info_sum;
   ppo_apply_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(a);
   p->launches += 1;
   CUDA_TRY(cudaGetLastError());
@@ -343,5 +352,124 @@ extern "C" int dronecu_ppo_set_state(dronecu_ppo* p, const float* d_moments, int
   const long long t = step;
   CUDA_TRY(cudaMemcpyAsync(p->d_step, &t, sizeof(t), cudaMemcpyHostToDevice, (cudaStream_t)stream));
   CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  return DRONECU_OK;
+}
+
+
+extern "C" int dronecu_ppo_set_info_accumulator(dronecu_ppo* p, float* d_info_sum) {
+  if (!p) return fail(DRONECU_ERR_INVALID, "null handle");
+  p->info_sum = d_info_sum;
+  return DRONECU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// data-parallel exchange over NVLink peer memory (csrc/ppo_dp.cuh)
+// ------------------------------------------------------------------------------------------------
+static_assert(sizeof(cudaIpcMemHandle_t) == DRONECU_IPC_HANDLE_BYTES, "IPC handle size");
+
+extern "C" int dronecu_ppo_dp_alloc(dronecu_ppo* p, int rank, int world, void* ipc_handle_out, void** d_mailbox_out) {
+  if (!p || world < 1 || world > kDpMaxWorld || rank < 0 || rank >= world)
+    return fail(DRONECU_ERR_INVALID, "dronecu_ppo_dp_alloc: bad rank / world (at most 16 ranks)");
+  if (p->dp_mail) return fail(DRONECU_ERR_INVALID, "dronecu_ppo_dp_alloc: already allocated");
+  DeviceGuard guard(p->device);
+  const size_t bytes = dp_mailbox_bytes(world);
+  CUDA_TRY(cudaMalloc(&p->dp_mail, bytes));
+  CUDA_TRY(cudaMemset(p->dp_mail, 0, bytes));
+  CUDA_TRY(cudaMalloc(&p->dp.seq, sizeof(unsigned long long)));
+  CUDA_TRY(cudaMemset(p->dp.seq, 0, sizeof(unsigned long long)));
+  CUDA_TRY(cudaMalloc(&p->dp.status, sizeof(int)));
+  CUDA_TRY(cudaMemset(p->dp.status, 0, sizeof(int)));
+  CUDA_TRY(cudaDeviceSynchronize());
+  p->dp.rank = rank; p->dp.world = 0;          // world is set by dronecu_ppo_dp_connect
+  p->dp.timeout_ns = 30ull * 1000000000ull;
+  if (ipc_handle_out) {
+    cudaIpcMemHandle_t h;
+    CUDA_TRY(cudaIpcGetMemHandle(&h, p->dp_mail));
+    std::memcpy(ipc_handle_out, &h, sizeof(h));
+  }
+  if (d_mailbox_out) *d_mailbox_out = p->dp_mail;
+  p->dp.mail[rank] = p->dp_mail;
+  (void)world;
+  return DRONECU_OK;
+}
+
+extern "C" int dronecu_ppo_dp_connect(dronecu_ppo* p, int world, const void* ipc_handles, void* const* d_mailboxes) {
+  if (!p || !p->dp_mail) return fail(DRONECU_ERR_INVALID, "dronecu_ppo_dp_connect: call dronecu_ppo_dp_alloc first");
+  if (world < 1 || world > kDpMaxWorld || p->dp.rank >= world) return fail(DRONECU_ERR_INVALID, "dronecu_ppo_dp_connect: bad world");
+  if (!ipc_handles && !d_mailboxes && world > 1) return fail(DRONECU_ERR_INVALID, "dronecu_ppo_dp_connect: no peers given");
+  DeviceGuard guard(p->device);
+  for (int r = 0; r < world; ++r) {
+    if (r == p->dp.rank) continue;
+    if (d_mailboxes) {                       // same process: raw device pointers (enable peer access when on another GPU)
+      void* ptr = d_mailboxes[r];
+      cudaPointerAttributes at;
+      CUDA_TRY(cudaPointerGetAttributes(&at, ptr));
+      if (at.type != cudaMemoryTypeDevice) return fail(DRONECU_ERR_INVALID, "dronecu_ppo_dp_connect: not a device pointer");
+      if (at.device != p->device) {
+        int can = 0;
+        CUDA_TRY(cudaDeviceCanAccessPeer(&can, p->device, at.device));
+        if (!can) return fail(DRONECU_ERR_UNSUPPORTED, "dronecu_ppo_dp_connect: no peer access between the devices");
+        cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CUDA_TRY(e);
+        cudaGetLastError();
+      }
+      p->dp.mail[r] = static_cast<float*>(ptr);
+    } else {
+      cudaIpcMemHandle_t h;
+      std::memcpy(&h, static_cast<const char*>(ipc_handles) + (size_t)r * DRONECU_IPC_HANDLE_BYTES, sizeof(h));
+      void* ptr = nullptr;
+      CUDA_TRY(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+      p->dp.mail[r] = static_cast<float*>(ptr);
+      p->dp_opened[r] = true;
+    }
+  }
+  CUDA_TRY(cudaFuncSetAttribute(ppo_apply_dp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * kGradLen)));
+  p->dp.world = world;
+  return DRONECU_OK;
+}
+
+extern "C" int dronecu_ppo_dp_set_timeout(dronecu_ppo* p, double seconds) {
+  if (!p || !(seconds > 0)) return fail(DRONECU_ERR_INVALID, "dronecu_ppo_dp_set_timeout: bad argument");
+  p->dp.timeout_ns = (unsigned long long)(seconds * 1e9);
+  return DRONECU_OK;
+}
+
+extern "C" int dronecu_ppo_dp_status(dronecu_ppo* p, int* h_status, int64_t* h_exchanges) {   // synchronises the device
+  if (!p || !p->dp_mail) return fail(DRONECU_ERR_INVALID, "dronecu_ppo_dp_status: data-parallel exchange not set up");
+  DeviceGuard guard(p->device);
+  int st = 0; unsigned long long seq = 0;
+  CUDA_TRY(cudaMemcpy(&st, p->dp.status, sizeof(st), cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(&seq, p->dp.seq, sizeof(seq), cudaMemcpyDeviceToHost));
+  if (h_status) *h_status = st;
+  if (h_exchanges) *h_exchanges = (int64_t)seq;
+  return DRONECU_OK;
+}
+
+extern "C" int dronecu_ppo_dp_allreduce_f64(dronecu_ppo* p, double* d_buf, int n, void* stream) {
+  if (!p || !d_buf || n <= 0 || n > kDpSlot / 2) return fail(DRONECU_ERR_INVALID, "dronecu_ppo_dp_allreduce_f64: bad argument (at most 5376 values)");
+  if (p->dp.world < 1) return fail(DRONECU_ERR_INVALID, "dronecu_ppo_dp_allreduce_f64: call dronecu_ppo_dp_connect first");
+  if (reinterpret_cast<uintptr_t>(d_buf) & 15) return fail(DRONECU_ERR_INVALID, "d_buf must be 16-byte aligned");
+  DeviceGuard guard(p->device);
+  dp_allreduce_f64_kernel<<<1, kDpBlock, 0, (cudaStream_t)stream>>>(p->dp, d_buf, n);
+  p->launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  return DRONECU_OK;
+}
+
+extern "C" int dronecu_ppo_apply_dp(dronecu_ppo* p, float* d_params, float* d_grad, float* d_info, void* stream) {
+  if (!p || !d_params || !d_grad) return fail(DRONECU_ERR_INVALID, "dronecu_ppo_apply_dp: bad argument");
+  if (p->dp.world < 1) return fail(DRONECU_ERR_INVALID, "dronecu_ppo_apply_dp: call dronecu_ppo_dp_connect first");
+  if (reinterpret_cast<uintptr_t>(d_grad) & 15) return fail(DRONECU_ERR_INVALID, "d_grad must be 16-byte aligned");
+  DeviceGuard guard(p->device);
+  AdamArgs a;
+  a.theta = d_params; a.grad = d_grad; a.m = p->moments; a.v = p->moments + kParams;
+  a.inv_count = 0.f;                       // unused: the denominator is the summed sample count
+  a.lr = p->cfg.learning_rate;
+  a.step = p->d_step;
+  a.beta1 = p->cfg.beta1; a.beta2 = p->cfg.beta2; a.eps = p->cfg.adam_eps; a.max_norm = p->cfg.max_grad_norm;
+  a.info = d_info; a.info_sum = p->info_sum;
+  ppo_apply_dp_kernel<<<1, kDpBlock, sizeof(float) * kGradLen, (cudaStream_t)stream>>>(p->dp, a, d_grad);
+  p->launches += 1;
+  CUDA_TRY(cudaGetLastError());
   return DRONECU_OK;
 }

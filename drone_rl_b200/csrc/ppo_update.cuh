@@ -454,7 +454,9 @@ struct AdamArgs {
   float inv_count;           // 1 / (global number of samples in the minibatch)
   float lr, beta1, beta2, eps, max_norm;
   long long* step;           // device-resident Adam step count (incremented here: the launch sequence is CUDA-graph capturable)
-  float* info;               // [kStats + 1]: mean statistics + pre-clip gradient norm
+  float* info;               // [kStats + 1]: mean statistics + pre-clip gradient norm of THIS step (nullable)
+  float* info_sum;           // [kStats + 2]: the same values ACCUMULATED over the steps + the number of steps (nullable):
+                             // SB3 logs the mean over all minibatches of PPO.train(), not the last one
 };
 
 // torch.nn.utils.clip_grad_norm_(max_norm) + torch.optim.Adam.step() on the flat vector (one CTA)
@@ -485,6 +487,11 @@ __global__ void __launch_bounds__(1024) ppo_apply_kernel(const AdamArgs A) {
       if (A.info) {
         for (int q = 0; q < kStats; ++q) A.info[q] = A.grad[kParams + q] * (q == 4 ? 1.0f : A.inv_count);
         A.info[kStats] = norm;
+      }
+      if (A.info_sum) {
+        for (int q = 0; q < kStats; ++q) A.info_sum[q] += A.grad[kParams + q] * (q == 4 ? 1.0f : A.inv_count);
+        A.info_sum[kStats] += norm;
+        A.info_sum[kStats + 1] += 1.0f;
       }
     }
   }

@@ -3,15 +3,21 @@ train.py:36-43, :63-68) with SB3's defaults, computed by the CUDA kernels behind
 
 Host side only orchestrates: ONE launch collects ``n_steps`` env steps for every env with the policy
 evaluated in-kernel (``dronecu_rollout_policy``), one computes GAE, and each minibatch is
-adv-stats -> grad -> [NCCL all-reduce] -> clip+Adam.  torch supplies device memory, the random
-permutation and ``torch.distributed``; no torch op touches the numerics.
+adv-stats -> grad -> [exchange over peer memory] -> clip+Adam.  torch supplies device memory and
+``torch.distributed``; no torch op touches the numerics.
 
 Data parallel (``torch.distributed`` initialised, one process per GPU): every rank owns a contiguous
-shard of global env ids and its own rollout buffers; per optimiser step the flat gradient (10,705
-float32 incl. statistics) and the three advantage sums are all-reduced, so the update equals the
-single-GPU update over the union of the shards.
+shard of global env ids and its own rollout buffers; per optimiser step the flat sum-form gradient (10,705
+float32 incl. statistics) is summed over the ranks and per epoch the advantage sums of its minibatches, so
+the update equals the single-GPU update over the union of the shards.  The exchange is
+``dp_backend="peer"`` (default): one kernel per optimiser step pushes the gradient into mailboxes in every
+peer's HBM over NVLink, waits on flags, sums in fixed rank order and runs clip + Adam (csrc/ppo_dp.cuh) -- no
+NCCL call on the data path, and the epoch stays one CUDA graph; ``"nccl"``: torch.distributed.all_reduce
+between the reduce and apply kernels (the round-1 path, kept for comparison).  torch.distributed is used for the
+set-up (exchange of IPC handles, barriers) either way.
 
-PARITY UNPINNED: SB3 is not in the reference tree; tests compare against oracle/ppo_oracle.py.
+PARITY: the primitives SB3 composes are pinned to torch's own (tests/test_ppo_oracle_torch_pin.py); the composition
+(SB3 itself) is not in the reference tree and not installable -- unpinned; tests compare against oracle/ppo_oracle.py.
 """
 from __future__ import annotations
 
@@ -40,24 +46,27 @@ SB3_NAMES = {"pi.W1": "mlp_extractor.policy_net.0.weight", "pi.b1": "mlp_extract
 
 
 def init_policy_params(seed: int = 0) -> torch.Tensor:
-    """SB3 ActorCriticPolicy initialisation: orthogonal weights (gain sqrt2 towers, 0.01 action head,
-    1 value head), zero biases, log_std = 0.  Flat float32 CPU vector [10697]."""
-    g = torch.Generator().manual_seed(seed)
-    gains = {"pi.W1": math.sqrt(2), "pi.W2": math.sqrt(2), "pi.W3": 0.01,
-             "vf.W1": math.sqrt(2), "vf.W2": math.sqrt(2), "vf.W3": 1.0}
-    flat, off = torch.zeros(POLICY_PARAMS, dtype=torch.float64), 0
-    for name, shape in _SHAPES:
-        n = int(np.prod(shape))
-        if name in gains:
-            rows, cols = shape
-            a = torch.randn((max(rows, cols), min(rows, cols)), generator=g, dtype=torch.float64)
-            q, r = torch.linalg.qr(a)
-            q = q * torch.sign(torch.diag(r))
-            if rows < cols:
-                q = q.t()
-            flat[off:off + n] = (q[:rows, :cols] * gains[name]).reshape(-1)
-        off += n
-    return flat.to(torch.float32)
+    """The initial parameters of SB3's ``ActorCriticPolicy`` for ``PPO("MlpPolicy", env, seed=seed)`` (reference
+    train.py:36-43), built from torch's own ``nn.Linear`` / ``nn.init.orthogonal_``: modules constructed in SB3's order
+    under ``torch.manual_seed(seed)`` (policy tower, value tower, action head, value head), then orthogonal weights
+    (gain sqrt2 towers, 0.01 action head, 1 value head), zero biases, log_std = 0.  The global torch RNG is left
+    untouched.  Flat float32 CPU vector [10697]."""
+    nn = torch.nn
+    with torch.random.fork_rng(devices=[]):
+        torch.manual_seed(seed)
+        pi = nn.Sequential(nn.Linear(15, 64), nn.Tanh(), nn.Linear(64, 64), nn.Tanh())
+        vf = nn.Sequential(nn.Linear(15, 64), nn.Tanh(), nn.Linear(64, 64), nn.Tanh())
+        action_net, value_net = nn.Linear(64, 4), nn.Linear(64, 1)
+        with torch.no_grad():
+            for layer, gain in ((pi[0], math.sqrt(2)), (pi[2], math.sqrt(2)), (vf[0], math.sqrt(2)), (vf[2], math.sqrt(2)),
+                                (action_net, 0.01), (value_net, 1.0)):
+                nn.init.orthogonal_(layer.weight, gain=gain)
+                layer.bias.fill_(0.0)
+    tensors = {"pi.W1": pi[0].weight, "pi.b1": pi[0].bias, "pi.W2": pi[2].weight, "pi.b2": pi[2].bias,
+               "pi.W3": action_net.weight, "pi.b3": action_net.bias,
+               "vf.W1": vf[0].weight, "vf.b1": vf[0].bias, "vf.W2": vf[2].weight, "vf.b2": vf[2].bias,
+               "vf.W3": value_net.weight, "vf.b3": value_net.bias, "log_std": torch.zeros(4)}
+    return torch.cat([tensors[name].detach().reshape(-1) for name, _ in _SHAPES]).to(torch.float32)
 
 
 def unpack_params(flat: torch.Tensor) -> dict:
@@ -98,7 +107,8 @@ class PPO:
                  gae_lambda: float = 0.95, clip_range: float = 0.2, ent_coef: float = 0.0, vf_coef: float = 0.5,
                  max_grad_norm: float = 0.5, learning_rate: float = 3e-4, normalize_advantage: bool = True,
                  seed: int = 0, device: int = 0, verbose: int = 0, policy_seed: Optional[int] = None,
-                 rollout_precision: str = "fp32", update_precision: str = "fp32", cuda_graph: Optional[bool] = None):
+                 rollout_precision: str = "fp32", update_precision: str = "fp32", cuda_graph: Optional[bool] = None,
+                 dp_backend: str = "peer"):
         self.lib = _lib.load()
         self.rank, self.world = 0, 1
         if torch.distributed.is_available() and torch.distributed.is_initialized():
@@ -131,13 +141,22 @@ class PPO:
         self._grad = torch.zeros(GRAD_LEN, dtype=torch.float32, device=self.device)
         self._adv_stats = torch.zeros(3, dtype=torch.float64, device=self.device)
         self._info = torch.zeros(9, dtype=torch.float32, device=self.device)
+        self._info_sum = torch.zeros(10, dtype=torch.float32, device=self.device)     # sums over the minibatches of one train()
+        _lib.check(self.lib.dronecu_ppo_set_info_accumulator(self._h, _ptr(self._info_sum)))
+        self._ev = torch.zeros(8, dtype=torch.float64, device=self.device)            # explained-variance moments
+        if dp_backend not in ("peer", "nccl"):
+            raise ValueError("dp_backend must be 'peer' (one exchange + clip + Adam kernel over NVLink peer memory) or 'nccl'")
+        self.dp_backend = dp_backend if self.world > 1 else None
+        if self.world > 1:
+            self._dp_setup()
         self._gen = torch.Generator(device=self.device).manual_seed(seed + 1)
         self.num_timesteps, self.n_updates = 0, 0
         self._perm, self._epochs_done = None, 0
         self.grad_events = None                   # set to [] to collect (start, end, samples) events per gradient launch
-        # One epoch's minibatch sequence (adv-stats -> grad -> reduce -> clip+Adam, x minibatches) as ONE CUDA graph: with
-        # SB3's defaults (batch 64) an epoch is hundreds of 10-microsecond kernels and the host launch rate is the bound.
-        # Default: on for small minibatches on a single GPU (NCCL all-reduces stay outside graphs here).
+        # One epoch's minibatch sequence (adv-stats -> grad -> reduce -> [exchange +] clip+Adam, x minibatches) as ONE CUDA
+        # graph: with SB3's defaults (batch 64) an epoch is hundreds of 10-microsecond kernels and the host launch rate is
+        # the bound.  Default: on for small minibatches, and always for data-parallel training over peer memory (the
+        # exchange is a kernel; only the "nccl" backend keeps its all-reduces outside graphs).
         self.cuda_graph = cuda_graph
         self._graph, self._graph_key, self._graph_launches = None, None, 0
         self._ep_stats = None
@@ -149,8 +168,56 @@ class PPO:
     # -- lifetime ------------------------------------------------------------------------------
     def close(self):
         if getattr(self, "_h", None):
+            if getattr(self, "dp_backend", None) == "peer" and torch.distributed.is_initialized():
+                torch.cuda.synchronize(self.device)
+                torch.distributed.barrier()       # no peer may still be writing into this rank's mailbox when it is freed
             self.lib.dronecu_ppo_destroy(self._h)
             self._h = None
+
+    # -- data-parallel set-up -------------------------------------------------------------------------
+    def _dp_setup(self):
+        """Every rank must hold the same number of transitions and minibatches (all ranks issue the same number of
+        exchanges); with the peer backend, allocate this rank's mailbox and map the peers' (CUDA IPC)."""
+        dist = torch.distributed
+        mine = torch.tensor([self.n_envs * self.n_steps, self.batch_size], dtype=torch.int64, device=self.device)
+        every = [torch.zeros_like(mine) for _ in range(self.world)]
+        dist.all_gather(every, mine)
+        if any(not torch.equal(e, mine) for e in every):
+            raise ValueError("data-parallel PPO: every rank needs the same n_envs * n_steps and batch_size, got "
+                             f"{[e.tolist() for e in every]}")
+        if self.dp_backend != "peer":
+            return
+        if self.world > _lib.DP_MAX_WORLD:
+            raise ValueError(f"dp_backend='peer' supports at most {_lib.DP_MAX_WORLD} ranks (one NVLink domain)")
+        handle = (C.c_ubyte * _lib.IPC_HANDLE_BYTES)()
+        _lib.check(self.lib.dronecu_ppo_dp_alloc(self._h, self.rank, self.world, handle, None), "dronecu_ppo_dp_alloc")
+        h = torch.tensor(list(bytes(handle)), dtype=torch.uint8, device=self.device)
+        allh = [torch.zeros_like(h) for _ in range(self.world)]
+        dist.all_gather(allh, h)
+        blob = b"".join(bytes(t.cpu().tolist()) for t in allh)
+        buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        _lib.check(self.lib.dronecu_ppo_dp_connect(self._h, self.world, buf, None), "dronecu_ppo_dp_connect")
+        torch.cuda.synchronize(self.device)
+        dist.barrier()                             # every mailbox is zeroed and mapped before the first push
+
+    def _allreduce_f64(self, t: torch.Tensor):
+        """In-place sum over the ranks of a small float64 device tensor (advantage / episode statistics)."""
+        if self.world == 1:
+            return
+        if self.dp_backend == "peer" and t.numel() <= 5376:
+            _lib.check(self.lib.dronecu_ppo_dp_allreduce_f64(self._h, _ptr(t), t.numel(), _stream_ptr(self.device)),
+                       "dronecu_ppo_dp_allreduce_f64")
+            self.launches += 1
+        else:
+            torch.distributed.all_reduce(t)
+
+    def dp_check(self):
+        """Raise if a peer-memory exchange timed out (a rank fell out of step or died)."""
+        if self.dp_backend == "peer":
+            st, n = C.c_int(), C.c_int64()
+            _lib.check(self.lib.dronecu_ppo_dp_status(self._h, C.byref(st), C.byref(n)))
+            if st.value:
+                raise _lib.DronecuError(f"rank {self.rank}: a data-parallel exchange timed out after {n.value} exchanges")
 
     def __del__(self):
         try:
@@ -185,8 +252,7 @@ class PPO:
             self._adv_stats.zero_()
             _lib.check(self.lib.dronecu_ppo_adv_stats(self._h, _ptr(b.adv), _ptr(index), first, m,
                                                       _ptr(self._adv_stats), st), "dronecu_ppo_adv_stats")
-            if self.world > 1:
-                torch.distributed.all_reduce(self._adv_stats)
+            self._allreduce_f64(self._adv_stats)
             stats_ptr = _ptr(self._adv_stats)
             self.launches += 2
         grad_fn = {"fp32": self.lib.dronecu_ppo_grad, "tf32": self.lib.dronecu_ppo_grad_tc,
@@ -200,10 +266,16 @@ class PPO:
         if self.grad_events is not None:
             ev[1].record()
             self.grad_events.append(ev)
-        if self.world > 1:
-            torch.distributed.all_reduce(self._grad)      # NCCL: 42.8 KB, the only collective of the data path
-        _lib.check(self.lib.dronecu_ppo_apply(self._h, _ptr(self.params), _ptr(self._grad),
-                                              1.0 / (m * self.world), _ptr(self._info), st), "dronecu_ppo_apply")
+        if self.dp_backend == "peer":
+            # ONE kernel: push to the peers' mailboxes over NVLink, wait, fixed-order sum, clip + Adam (csrc/ppo_dp.cuh)
+            _lib.check(self.lib.dronecu_ppo_apply_dp(self._h, _ptr(self.params), _ptr(self._grad), _ptr(self._info), st),
+                       "dronecu_ppo_apply_dp")
+        else:
+            if self.world > 1:
+                torch.distributed.all_reduce(self._grad)      # NCCL: 42.8 KB
+            # every rank holds m samples of this minibatch (checked in _dp_setup)
+            _lib.check(self.lib.dronecu_ppo_apply(self._h, _ptr(self.params), _ptr(self._grad),
+                                                  1.0 / (m * self.world), _ptr(self._info), st), "dronecu_ppo_apply")
         self.launches += 3
         self.n_updates += 1
 
@@ -233,6 +305,7 @@ class PPO:
         if self._perm is None or self._perm.numel() != B:
             self._perm = torch.empty(B, dtype=torch.int32, device=self.device)
         perm = self._perm
+        self._info_sum.zero_()
         for _ in range(self.n_epochs):
             # SB3: np.random.permutation(B) per epoch; here a keyed bijection evaluated on the device (no sort)
             _lib.check(self.lib.dronecu_minibatch_permutation(self.device.index, B, self.seed + 1, self._epochs_done,
@@ -249,30 +322,63 @@ class PPO:
                 _lib.check(self.lib.dronecu_ppo_adv_stats_epoch(self._h, _ptr(self.buf.adv), _ptr(perm), B, self.batch_size,
                                                                 _ptr(ep_stats), _stream_ptr(self.device)), "dronecu_ppo_adv_stats_epoch")
                 self.launches += 2
-                if self.world > 1:
-                    torch.distributed.all_reduce(ep_stats)
-            use_graph = self.cuda_graph if self.cuda_graph is not None else (self.batch_size <= 16384 and B // self.batch_size >= 4)
-            if use_graph and self.world == 1 and self.grad_events is None:
+                self._allreduce_f64(ep_stats)
+            use_graph = self.cuda_graph if self.cuda_graph is not None else (
+                (self.batch_size <= 16384 and B // self.batch_size >= 4) or self.dp_backend == "peer")
+            if use_graph and self.dp_backend != "nccl" and self.grad_events is None:
                 self._epoch_graph(perm, B, ep_stats)
                 continue
             for k, start in enumerate(range(0, B, self.batch_size)):
                 m = min(self.batch_size, B - start)
                 self._minibatch(perm[start:start + m], 0, m, None if ep_stats is None else ep_stats[k])
-        info = self._info.cpu().numpy()
-        self.logger_values.update({"train/policy_gradient_loss": float(info[0]), "train/value_loss": float(info[1]),
-                                   "train/approx_kl": float(info[2]), "train/clip_fraction": float(info[3]),
-                                   "train/loss": float(info[0] + self.cfg.vf_coef * info[1]),
-                                   "train/grad_norm": float(info[8]), "train/n_updates": self.n_updates,
-                                   "train/std": float(torch.exp(self.params[-4:]).mean())})
+        # SB3 logs the MEAN over all minibatches of all epochs (policy_gradient_loss, value_loss, approx_kl, clip_fraction,
+        # entropy_loss), the LAST minibatch's total loss, and the explained variance of the value estimates over the buffer
+        ev = self._explained_variance()
+        acc = torch.cat([self._info_sum, self._info]).cpu().numpy()
+        sums, last = acc[:10], acc[10:]
+        n_upd = max(float(sums[9]), 1.0)
+        log_std = self.params[-4:]
+        entropy_loss = -float((0.5 + 0.5 * math.log(2.0 * math.pi) + log_std).sum())
+        self.logger_values.update({"train/policy_gradient_loss": float(sums[0] / n_upd), "train/value_loss": float(sums[1] / n_upd),
+                                   "train/approx_kl": float(sums[2] / n_upd), "train/clip_fraction": float(sums[3] / n_upd),
+                                   "train/entropy_loss": entropy_loss,
+                                   "train/loss": float(last[0] + self.cfg.ent_coef * entropy_loss + self.cfg.vf_coef * last[1]),
+                                   "train/grad_norm": float(sums[8] / n_upd), "train/explained_variance": ev,
+                                   "train/n_updates": self.n_updates, "train/clip_range": float(self.cfg.clip_range),
+                                   "train/learning_rate": float(self.cfg.learning_rate),
+                                   "train/std": float(torch.exp(log_std).mean())})
+        self.dp_check()
 
-    def learn(self, total_timesteps: int, log_interval: int = 1, callback=None):
+    def _explained_variance(self) -> float:
+        """SB3's ``explained_variance(values, returns)`` over the whole rollout buffer (all ranks): 1 - Var[ret - value] /
+        Var[ret] -- logging only, from moments summed on the device."""
+        y, d = self.buf.ret.reshape(-1), (self.buf.ret - self.buf.value).reshape(-1)
+        (vy, my), (vd, md) = torch.var_mean(y, unbiased=False), torch.var_mean(d, unbiased=False)
+        n = float(y.numel())
+        m = torch.stack([my, vy + my * my, md, vd + md * md]).double() * n          # sums and sums of squares
+        self._ev[0] = n
+        self._ev[1:5] = m
+        self._allreduce_f64(self._ev)
+        n, sy, syy, sd, sdd = self._ev[:5].tolist()
+        var_y, var_d = syy / n - (sy / n) ** 2, sdd / n - (sd / n) ** 2
+        return float("nan") if var_y == 0 else 1.0 - var_d / var_y
+
+    def learn(self, total_timesteps: int, log_interval: int = 1, callback=None, reset_num_timesteps: bool = True):
+        """SB3 ``learn``: collect / train until ``total_timesteps`` MORE transitions have been gathered.  As in SB3,
+        ``reset_num_timesteps=True`` (the default) restarts the counter, so ``PPO.load("dd.zip", env).learn(2e6)``
+        (reference train.py:22-30, :63-68) trains for another 2e6 steps; ``False`` continues the counter (and the
+        logging x-axis) of the loaded model and trains ``total_timesteps`` on top of it."""
+        start = 0 if reset_num_timesteps else self.num_timesteps
+        if reset_num_timesteps:
+            self.num_timesteps = 0
+        total_timesteps = start + int(total_timesteps)
         t0, it = time.time(), 0
         while self.num_timesteps < total_timesteps:
             self.collect_rollouts()
             st = self.batch.episode_stats(reset=True)
             if self.world > 1:
-                v = torch.tensor([st["return_sum"], float(st["length_sum"]), float(st["episodes"])],
-                                 dtype=torch.float64, device=self.device)
+                v = self._ev[5:8]
+                v.copy_(torch.tensor([st["return_sum"], float(st["length_sum"]), float(st["episodes"])], dtype=torch.float64))
                 torch.distributed.all_reduce(v)
                 st["ep_rew_mean"] = float(v[0] / v[2]) if v[2] > 0 else float("nan")
                 st["ep_len_mean"] = float(v[1] / v[2]) if v[2] > 0 else float("nan")
@@ -280,7 +386,7 @@ class PPO:
             it += 1
             self.logger_values.update({"rollout/ep_rew_mean": st["ep_rew_mean"], "rollout/ep_len_mean": st["ep_len_mean"],
                                        "time/iterations": it, "time/total_timesteps": self.num_timesteps,
-                                       "time/fps": int(self.num_timesteps / max(time.time() - t0, 1e-9))})
+                                       "time/fps": int((self.num_timesteps - start) / max(time.time() - t0, 1e-9))})
             if callback is not None and callback(self) is False:
                 break
             if self.verbose and self.rank == 0 and it % log_interval == 0:
@@ -327,6 +433,7 @@ class PPO:
         return {"params": self.params.cpu(), "adam": mom.cpu(), "adam_step": step.value,
                 "num_timesteps": self.num_timesteps, "n_updates": self.n_updates, "epochs_done": self._epochs_done,
                 "env_state": self.batch.get_state(), "env_global_step": self.batch.global_step,
+                "env_offset": int(self.batch.env_offset), "world": self.world,
                 "sb3_policy": {SB3_NAMES[k]: v.clone() for k, v in unpack_params(self.params.cpu()).items()}}
 
     def load_state_dict(self, sd: dict, load_env: bool = True):
@@ -336,9 +443,15 @@ class PPO:
         torch.cuda.synchronize(self.device)
         self.num_timesteps, self.n_updates = sd["num_timesteps"], sd["n_updates"]
         self._epochs_done = int(sd.get("epochs_done", 0))
-        if load_env and "env_state" in sd and sd["env_state"]["pos"].shape[0] == self.n_envs:
+        # the env / curriculum / RNG state belongs to ONE shard of global env ids: restore it only onto the same shard
+        # (a data-parallel run writes one archive per rank: see save()); otherwise the envs start fresh
+        self.env_state_restored = False
+        if (load_env and "env_state" in sd and sd["env_state"]["pos"].shape[0] == self.n_envs
+                and int(sd.get("env_offset", self.batch.env_offset)) == int(self.batch.env_offset)
+                and int(sd.get("world", self.world)) == self.world):
             self.batch.set_state(**sd["env_state"])
             self.batch.global_step = sd.get("env_global_step", self.batch.global_step)
+            self.env_state_restored = True
 
     def save(self, path: str):
         """SB3 ``model.save(path)`` (train.py:70): no suffix -> ``path + ".zip"``, an archive in SB3's layout
@@ -348,12 +461,18 @@ class PPO:
             return
         from . import sb3_zip
         sd = self.state_dict()
+        if self.world > 1 and self.rank > 0:
+            # data parallel: policy and Adam state are replicas (rank 0's archive holds them); the env / curriculum /
+            # Philox state differs per shard -> every other rank writes its shard next to the archive
+            base = path[:-4] if path.endswith(".zip") else path
+            torch.save({k: sd[k] for k in ("env_state", "env_global_step", "env_offset", "world")}, f"{base}.env.rank{self.rank}.pt")
+            return
         hyper = {"n_steps": self.n_steps, "batch_size": self.batch_size, "n_epochs": self.n_epochs, "gamma": self.gamma,
                  "gae_lambda": self.gae_lambda, "learning_rate": float(self.cfg.learning_rate),
                  "clip_range": float(self.cfg.clip_range), "ent_coef": float(self.cfg.ent_coef),
                  "vf_coef": float(self.cfg.vf_coef), "max_grad_norm": float(self.cfg.max_grad_norm),
                  "n_envs": self.n_envs, "num_timesteps": self.num_timesteps, "_n_updates": self.n_updates, "seed": self.seed}
-        extra = {k: sd[k] for k in ("num_timesteps", "n_updates", "epochs_done", "env_state", "env_global_step")}
+        extra = {k: sd[k] for k in ("num_timesteps", "n_updates", "epochs_done", "env_state", "env_global_step", "env_offset", "world")}
         sb3_zip.export_zip(path if path.endswith(".zip") else path + ".zip", sd["params"], sd["adam"], sd["adam_step"],
                            hyper, extra)
 
@@ -381,5 +500,10 @@ class PPO:
               "n_updates": int(z["hyper"].get("_n_updates", 0) or 0)}
         if z["extra"]:
             sd.update(z["extra"])
+        if model.world > 1 and model.rank > 0:          # this rank's env shard, written by save() next to the archive
+            side = f"{path[:-4]}.env.rank{model.rank}.pt"
+            sd.pop("env_state", None)
+            if os.path.isfile(side):
+                sd.update(torch.load(side, weights_only=False))
         model.load_state_dict(sd)
         return model

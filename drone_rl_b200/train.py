@@ -183,7 +183,8 @@ def main(argv=None):
     torch.cuda.synchronize()
     if rank == 0:
         print("Wall-clock per iter:", time.time() - t0)        # train.py:46-53 prints the same probe
-    model.num_timesteps = model.num_timesteps - n_steps * args.n_envs * world   # the probe rollout is not counted
+    # the probe is not counted (learn() restarts the counter); it does advance the envs by one rollout, as the reference's
+    # probe advances its env by one step (train.py:46-50)
 
     logger = cb = None
     if rank == 0:
@@ -197,9 +198,10 @@ def main(argv=None):
             logger.dump(dict(m.logger_values), m.num_timesteps)
         return True
 
-    model.learn(total_timesteps=int(args.total_timesteps) + model.num_timesteps, callback=on_iteration)
+    # SB3 semantics (reset_num_timesteps=True): total_timesteps MORE steps, also after a resume (train.py:22-30, :63-68)
+    model.learn(total_timesteps=int(args.total_timesteps), callback=on_iteration)
+    model.save(args.save)            # rank 0: the archive; other ranks: their env / curriculum shard next to it
     if rank == 0:
-        model.save(args.save)
         logger.close()
         print(f"saved {args.save}.zip; run dir {logger.run_dir}")
     model.close()

@@ -296,10 +296,46 @@ int dronecu_ppo_debug_buffer(dronecu_ppo* ppo, float* d_dbg);
  * [policy_loss, value_loss, approx_kl, clip_fraction, count, -, -, -, grad_norm]. */
 int dronecu_ppo_apply(dronecu_ppo* ppo, float* d_params, const float* d_grad, double inv_count, float* d_info,
                       void* stream);
+/* d_info_sum (nullable, caller-owned, float32 [10]): from now on every dronecu_ppo_apply / dronecu_ppo_apply_dp ADDS
+ * its [policy_loss, value_loss, approx_kl, clip_fraction, count, -, -, -, grad_norm] and 1 (number of steps) into it --
+ * SB3's PPO.train() logs the mean over all minibatches of all epochs, not the last minibatch's values. */
+int dronecu_ppo_set_info_accumulator(dronecu_ppo* ppo, float* d_info_sum);
 int64_t dronecu_ppo_num_updates(const dronecu_ppo* ppo);
 /* Adam state access for checkpoints: copies [m | v] (2 * DRONECU_POLICY_PARAMS floats) device <-> device. */
 int dronecu_ppo_get_state(dronecu_ppo* ppo, float* d_moments, int64_t* h_step, void* stream);
 int dronecu_ppo_set_state(dronecu_ppo* ppo, const float* d_moments, int64_t step, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Data-parallel update over NVLink peer memory (csrc/ppo_dp.cuh).  The reference is single-process (train.py:33-43:
+ * one env, device="cpu"); this is the exchange north_star's configs[4] adds ("NCCL grad allreduce"), done as ONE
+ * kernel per optimiser step: every rank pushes its 42.8 KB sum-form gradient into a mailbox slot in each peer's HBM,
+ * publishes a flag (st.release.sys), waits for the flags of all ranks on its own mailbox, sums the slots in fixed rank
+ * order (bit-identical on every rank) and runs clip_grad_norm_ + Adam.  Plain launches on the caller's stream:
+ * CUDA-graph capturable, no host synchronisation, no NCCL call per step.
+ *
+ * Set-up, once per optimiser handle: every rank calls dronecu_ppo_dp_alloc, the 64-byte IPC handles are exchanged by
+ * the host (torch.distributed all_gather in drone_rl_b200/ppo.py), then dronecu_ppo_dp_connect maps the peers'
+ * mailboxes (cudaIpcOpenMemHandle; within one process pass the raw mailbox pointers instead).  A host barrier must
+ * separate connect from the first exchange, and the last exchange from dronecu_ppo_destroy.
+ * ---------------------------------------------------------------------------------------------- */
+#define DRONECU_IPC_HANDLE_BYTES 64
+#define DRONECU_DP_MAX_WORLD 16
+int dronecu_ppo_dp_alloc(dronecu_ppo* ppo, int rank, int world, void* ipc_handle_out /* [64], nullable */,
+                         void** d_mailbox_out /* nullable */);
+/* ipc_handles: [world][64] bytes (entry `rank` ignored), or NULL with d_mailboxes[world] = raw device pointers of
+ * mailboxes allocated in THIS process (peer access is enabled as needed). */
+int dronecu_ppo_dp_connect(dronecu_ppo* ppo, int world, const void* ipc_handles, void* const* d_mailboxes);
+/* A rank that waits longer than this for its peers (default 30 s) raises the status flag instead of hanging the GPU. */
+int dronecu_ppo_dp_set_timeout(dronecu_ppo* ppo, double seconds);
+/* *h_status: 0 = ok, 1 = an exchange timed out (every result after it is invalid); *h_exchanges: exchanges done. */
+int dronecu_ppo_dp_status(dronecu_ppo* ppo, int* h_status, int64_t* h_exchanges);
+/* In-place sum over the ranks of n <= 5376 float64 values (advantage / episode statistics), rank order fixed. */
+int dronecu_ppo_dp_allreduce_f64(dronecu_ppo* ppo, double* d_buf, int n, void* stream);
+/* dronecu_ppo_apply for data-parallel training: d_grad (the LOCAL output of dronecu_ppo_grad*, 16-byte aligned) is
+ * replaced by its sum over the ranks, the denominator is the summed sample count d_grad[DRONECU_POLICY_PARAMS + 4]
+ * (ranks may hold minibatches of different sizes), then clip + Adam as dronecu_ppo_apply.  Every rank must call it
+ * the same number of times. */
+int dronecu_ppo_apply_dp(dronecu_ppo* ppo, float* d_params, float* d_grad, float* d_info, void* stream);
 
 #ifdef __cplusplus
 }

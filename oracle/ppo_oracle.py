@@ -47,25 +47,43 @@ def offsets():
     return out
 
 
+# SB3 builds the modules in this order (MlpExtractor: policy_net then value_net; then action_net, value_net) and
+# re-initialises them in the order of ActorCriticPolicy._build's module_gains dict.
+_BUILD_ORDER = ["pi.W1", "pi.W2", "vf.W1", "vf.W2", "pi.W3", "vf.W3"]
+_INIT_ORDER = [("pi.W1", math.sqrt(2)), ("pi.W2", math.sqrt(2)), ("vf.W1", math.sqrt(2)), ("vf.W2", math.sqrt(2)),
+               ("pi.W3", 0.01), ("vf.W3", 1.0)]
+
+
+def orthogonal(rows: int, cols: int, gain: float, g: torch.Generator) -> torch.Tensor:
+    """torch.nn.init.orthogonal_ restated on a float32 [rows, cols] weight (pinned against torch's own in
+    tests/test_ppo_oracle_torch_pin.py): N(0,1) draws in the weight's own shape, transposed when rows < cols,
+    reduced QR, Q's columns signed by diag(R), transposed back, scaled by the gain."""
+    a = torch.empty(rows, cols, dtype=torch.float32).normal_(0, 1, generator=g)
+    if rows < cols:
+        a = a.t()
+    q, r = torch.linalg.qr(a)
+    q = q * torch.sign(torch.diag(r, 0))
+    if rows < cols:
+        q = q.t()
+    return q * gain
+
+
 def init_params(seed: int = 0, dtype=torch.float32) -> torch.Tensor:
-    """SB3 ActorCriticPolicy init: orthogonal weights (gain sqrt(2) towers, 0.01 action head,
-    1.0 value head), zero biases, log_std = 0.  Returns the flat vector."""
+    """What ``PPO("MlpPolicy", env, seed=seed)`` (reference train.py:36-43) holds after construction, restated:
+    SB3 seeds torch's global generator, builds the six nn.Linear (each draws its default kaiming-uniform weight and
+    uniform bias -- consumed here so that the stream position matches), then ActorCriticPolicy re-initialises them
+    orthogonally (gain sqrt(2) towers, 0.01 action head, 1.0 value head) with zero biases; log_std = 0.
+    Returns the flat vector."""
     g = torch.Generator().manual_seed(seed)
-    flat = torch.zeros(N_PARAMS, dtype=torch.float64)
-    gains = {"pi.W1": math.sqrt(2), "pi.W2": math.sqrt(2), "pi.W3": 0.01,
-             "vf.W1": math.sqrt(2), "vf.W2": math.sqrt(2), "vf.W3": 1.0}
-    for name, (off, shape) in offsets().items():
-        if name in gains:
-            w = torch.empty(shape, dtype=torch.float64)
-            # torch.nn.init.orthogonal_ restated with an explicit generator
-            rows, cols = shape
-            a = torch.randn((max(rows, cols), min(rows, cols)), generator=g, dtype=torch.float64)
-            q, r = torch.linalg.qr(a)
-            q = q * torch.sign(torch.diag(r))
-            if rows < cols:
-                q = q.t()
-            w.copy_(q[:rows, :cols] * gains[name])
-            flat[off:off + w.numel()] = w.reshape(-1)
+    offs = offsets()
+    for name in _BUILD_ORDER:                       # nn.Linear.reset_parameters: weight then bias
+        rows, cols = offs[name][1]
+        torch.empty(rows, cols, dtype=torch.float32).uniform_(-1, 1, generator=g)
+        torch.empty(rows, dtype=torch.float32).uniform_(-1, 1, generator=g)
+    flat = torch.zeros(N_PARAMS, dtype=torch.float32)
+    for name, gain in _INIT_ORDER:
+        off, (rows, cols) = offs[name]
+        flat[off:off + rows * cols] = orthogonal(rows, cols, gain, g).reshape(-1)
     return flat.to(dtype)
 
 

@@ -1,9 +1,10 @@
 """TEST INFRASTRUCTURE: import the *unmodified* reference env modules as a live oracle.
 
-Only usable where ``/root/reference`` exists (the build container).  It is used by
-``tests/golden/make_golden.py`` to generate the committed fixtures and by the
-``not gpu`` tests that pin ``oracle/drone_oracle.py`` against the real thing; nothing
-that runs on the GPU box may depend on it.
+Usable where ``/root/reference`` exists (the build container) or where ``oracle/make_ref.py`` staged a
+byte-for-byte copy under ``oracle/_ref/`` (git-ignored; travels to the GPU box with the snapshot).  It is used by
+``tests/golden/make_golden.py`` to generate the committed fixtures, by the ``not gpu`` tests that pin
+``oracle/drone_oracle.py`` against the real thing, and by ``bench.py``'s CPU legs (``--impl reference``,
+``cpu_baseline`` kind "reference").  The ``-m gpu`` tests and ``smoke()`` never depend on it.
 
 The reference imports two third-party packages at module top level that are absent in
 this image: ``gym`` (drone.py:2-3, vectorized_drone.py:2-3 -- only ``gym.Env`` and
@@ -17,11 +18,27 @@ import os
 import sys
 import types
 
-REFERENCE_DIR = os.environ.get("DRONE_REFERENCE_DIR", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "reference_py.zip")   # written by oracle/make_ref.py
+
+
+def _find_reference() -> str:
+    if "DRONE_REFERENCE_DIR" in os.environ:
+        return os.environ["DRONE_REFERENCE_DIR"]
+    if os.path.isfile("/root/reference/drone.py"):
+        return "/root/reference"
+    return _STAGED                  # the GPU box: the byte-for-byte archive that travelled with the snapshot (zipimport)
+
+
+REFERENCE_DIR = _find_reference()
 
 
 def available() -> bool:
-    return os.path.isfile(os.path.join(REFERENCE_DIR, "drone.py"))
+    return os.path.isfile(REFERENCE_DIR) or os.path.isfile(os.path.join(REFERENCE_DIR, "drone.py"))
+
+
+def kind() -> str:
+    """Where the live reference comes from: "tree" (/root/reference) or "staged" (oracle/_ref archive)."""
+    return "staged" if os.path.isfile(REFERENCE_DIR) else "tree"
 
 
 class _Box:

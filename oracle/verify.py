@@ -33,6 +33,10 @@ def check_rollout(obs0, actions, next_obs, reward, done, *, spec=do.SINGLE, seed
     step = np.zeros(n, dtype=np.int64) if step0 is None else np.broadcast_to(np.asarray(step0, dtype=np.int64), (n,)).copy()
     prev = np.asarray(obs0, dtype=np.float32)
     worst, borderline, n_done, n_sing = 0.0, 0, 0, 0
+    # the tolerance has a unit floor (1e-5 * max(|ref|, 1)); to make the floor visible also track the worst PURE relative
+    # error |got - ref| / |ref| -- over all finite non-zero reference entries outside the near-singular rows, and over those
+    # with |ref| >= 1e-3 (below that the quantity is a difference of O(1) terms and its relative error is cancellation)
+    pure = {"all": (0.0, 0.0), "ref_ge_1e-3": (0.0, 0.0), "ref_ge_1": (0.0, 0.0)}
     with np.errstate(all="ignore"):
         for k in range(K):
             p64 = prev.astype(np.float64)
@@ -67,6 +71,15 @@ def check_rollout(obs0, actions, next_obs, reward, done, *, spec=do.SINGLE, seed
                 ratio = float(np.max(err / bound))
                 worst = max(worst, ratio)
                 assert ratio <= 1.0, f"obs outside tolerance at step {k}: err/bound {ratio:.3g}"
+            reg = fin & ~sing[:, None] & (ref_obs != 0)
+            if reg.any():
+                e, r = np.abs(got_obs - ref_obs)[reg], np.abs(ref_obs)[reg]
+                for name, lo in (("all", 0.0), ("ref_ge_1e-3", 1e-3), ("ref_ge_1", 1.0)):
+                    m = r >= lo
+                    if m.any():
+                        j = int(np.argmax(e[m] / r[m]))
+                        if e[m][j] / r[m][j] > pure[name][0]:
+                            pure[name] = (float(e[m][j] / r[m][j]), float(r[m][j]))
             both = d_got == d_ref
             rfin = np.isfinite(rew) & both
             rerr = np.abs(np.asarray(reward[k], dtype=np.float64) - rew)[rfin]
@@ -88,4 +101,5 @@ def check_rollout(obs0, actions, next_obs, reward, done, *, spec=do.SINGLE, seed
                 assert np.array_equal(np.asarray(next_obs[k])[rows], ref_reset[:, :D]), f"reset obs at step {k}"
             prev = np.asarray(next_obs[k], dtype=np.float32)
     return {"worst_err_over_bound": worst, "borderline_done": borderline, "dones": n_done,
-            "near_singular_rows": n_sing, "transitions": K * n}
+            "near_singular_rows": n_sing, "transitions": K * n,
+            "worst_pure_relative": {k: {"rel_err": v[0], "at_abs_ref": v[1]} for k, v in pure.items()}}
