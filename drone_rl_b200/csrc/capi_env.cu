@@ -166,14 +166,14 @@ extern "C" int dronecu_create(const dronecu_config* cfg, int device, int64_t n_e
   return DRONECU_OK;
 }
 
+static void free_io(dronecu_env* e);
+
 extern "C" int dronecu_destroy(dronecu_env* e) {
   if (!e) return DRONECU_OK;
   DeviceGuard guard(e->device);
   cudaDeviceSynchronize();
   cudaFree(e->planes); cudaFree(e->stats);
-  cudaFree(e->d_act); cudaFree(e->d_obs); cudaFree(e->d_rew); cudaFree(e->d_term);
-  cudaFree(e->d_done); cudaFree(e->d_trunc); cudaFree(e->d_mask); cudaFree(e->d_ep_r); cudaFree(e->d_ep_l);
-  cudaFree(e->d_view_f); cudaFree(e->d_view_i);
+  free_io(e);
   if (e->io_stream) cudaStreamDestroy(e->io_stream);
   if (e->io_stream2) cudaStreamDestroy(e->io_stream2);
   cudaGetLastError();
@@ -242,12 +242,20 @@ extern "C" int dronecu_step(dronecu_env* e, const float* d_actions, const dronec
 // The *_host entry points run on the handle's own stream.  They first wait for everything
 // already queued on the device (work the caller enqueued on other streams through the
 // device-pointer entry points), and they return only after their own copies have landed.
-static int ensure_io(dronecu_env* e) {
-  CUDA_TRY(cudaDeviceSynchronize());
-  if (e->io_stream) return DRONECU_OK;
+static void free_io(dronecu_env* e) {
+  cudaFree(e->d_act); cudaFree(e->d_obs); cudaFree(e->d_rew); cudaFree(e->d_term);
+  cudaFree(e->d_done); cudaFree(e->d_trunc); cudaFree(e->d_mask); cudaFree(e->d_ep_r); cudaFree(e->d_ep_l);
+  cudaFree(e->d_view_f); cudaFree(e->d_view_i);
+  e->d_act = e->d_obs = e->d_rew = e->d_term = e->d_ep_r = e->d_view_f = nullptr;
+  e->d_done = e->d_trunc = e->d_mask = nullptr;
+  e->d_ep_l = e->d_view_i = nullptr;
+  cudaGetLastError();
+}
+
+static int alloc_io(dronecu_env* e) {
   const size_t n = (size_t)e->n, D = (size_t)e->cfg.obs_dim;
-  CUDA_TRY(cudaStreamCreateWithFlags(&e->io_stream, cudaStreamNonBlocking));
-  CUDA_TRY(cudaStreamCreateWithFlags(&e->io_stream2, cudaStreamNonBlocking));
+  if (!e->io_stream) CUDA_TRY(cudaStreamCreateWithFlags(&e->io_stream, cudaStreamNonBlocking));
+  if (!e->io_stream2) CUDA_TRY(cudaStreamCreateWithFlags(&e->io_stream2, cudaStreamNonBlocking));
   CUDA_TRY(cudaMalloc(&e->d_act, n * 4 * sizeof(float)));
   CUDA_TRY(cudaMalloc(&e->d_obs, n * D * sizeof(float)));
   CUDA_TRY(cudaMalloc(&e->d_term, n * D * sizeof(float)));
@@ -259,6 +267,17 @@ static int ensure_io(dronecu_env* e) {
   CUDA_TRY(cudaMalloc(&e->d_ep_l, n * sizeof(int32_t)));
   CUDA_TRY(cudaMalloc(&e->d_view_f, n * 16 * sizeof(float)));
   CUDA_TRY(cudaMalloc(&e->d_view_i, n * 3 * sizeof(int32_t)));
+  return DRONECU_OK;
+}
+
+static int ensure_io(dronecu_env* e) {
+  CUDA_TRY(cudaDeviceSynchronize());
+  if (e->io_ready) return DRONECU_OK;
+  // a failed allocation (out of memory at large n) must not leave a half-built set behind: the next call would
+  // otherwise run with NULL staging buffers.  Free whatever exists, report, and let the caller retry.
+  const int rc = alloc_io(e);
+  if (rc != DRONECU_OK) { free_io(e); return rc; }
+  e->io_ready = true;
   return DRONECU_OK;
 }
 

@@ -18,6 +18,7 @@ struct dronecu_env {
   uint64_t launches;
   uint64_t env_steps;
   // device + stream used by the *_host entry points (lazily created)
+  bool io_ready;             // every staging buffer below exists (set only after ALL allocations succeeded)
   cudaStream_t io_stream;
   cudaStream_t io_stream2;   // second stream: chunked step_host overlaps H2D, kernel and D2H
   float *d_act, *d_obs, *d_rew, *d_term;
