@@ -216,3 +216,13 @@ def test_two_rank_training_equals_one_rank_on_the_union(drl, precision):
     for k in ("train/value_loss", "train/policy_gradient_loss", "train/approx_kl", "train/explained_variance"):
         assert abs(peer["logs"][k] - model.logger_values[k]) <= 1e-4 * max(1.0, abs(model.logger_values[k])), k
     model.close()
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 4, reason="needs at least four GPUs (gpurun --gpus 4 / 8)")
+def test_all_ranks_hold_identical_replicas(drl):
+    """Every GPU of the box as one rank: after two PPO iterations (the second replays the captured epoch graphs) the
+    parameter replicas are bit-identical -- the fixed-rank-order sum of the peer exchange at world = 4 / 8."""
+    world = 8 if torch.cuda.device_count() >= 8 else 4
+    out = _run_dp("peer", "bf16", world=world)
+    assert out["identical"] and out["graph"]
+    assert torch.isfinite(out["params"]).all()

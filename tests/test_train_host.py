@@ -191,3 +191,92 @@ def test_pillow_renderer_scene_and_gif(tmp_path):
     rec.finish()
     g = Image.open(tmp_path / "run.gif")
     assert g.is_animated and g.n_frames == 5 and g.info["duration"] == 50
+
+
+class _SB3ShapedPolicy(torch.nn.Module):
+    """A genuine torch module registered the way SB3 2.x's ``ActorCriticPolicy._build`` registers its members for
+    ``MlpPolicy`` on Box(15) -> Box(4): ``mlp_extractor`` (policy_net / value_net: Linear-Tanh-Linear-Tanh), then
+    ``action_net`` + the ``log_std`` parameter (DiagGaussianDistribution.proba_distribution_net), then ``value_net``.
+    ``parameters()`` therefore yields log_std first (the module's own parameter), then the children in that order."""
+
+    def __init__(self):
+        super().__init__()
+        nn = torch.nn
+
+        class MlpExtractor(nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.policy_net = nn.Sequential(nn.Linear(15, 64), nn.Tanh(), nn.Linear(64, 64), nn.Tanh())
+                self.value_net = nn.Sequential(nn.Linear(15, 64), nn.Tanh(), nn.Linear(64, 64), nn.Tanh())
+        self.mlp_extractor = MlpExtractor()
+        self.action_net = nn.Linear(64, 4)
+        self.log_std = nn.Parameter(torch.zeros(4))
+        self.value_net = nn.Linear(64, 1)
+
+    def forward(self, x):
+        return self.action_net(self.mlp_extractor.policy_net(x)), self.value_net(self.mlp_extractor.value_net(x)).flatten()
+
+
+def test_sb3_zip_from_a_genuine_module_and_optimizer(tmp_path):
+    """The closest thing to a real SB3 archive that can be built without SB3: ``policy.pth`` = ``state_dict()`` of a genuine
+    nn.Module with SB3's member names, ``policy.optimizer.pth`` = ``state_dict()`` of a genuine ``torch.optim.Adam`` that
+    has taken steps on it (layout of stable-baselines3 2.x ``save_to_zip_file``).  import_zip must map both onto the flat
+    vectors; export_zip must write members the genuine module / optimiser load back strictly."""
+    from oracle import ppo_oracle as po
+    torch.manual_seed(9)
+    pol = _SB3ShapedPolicy()
+    assert [n for n, _ in pol.named_parameters()] == sb3_zip.SB3_PARAM_ORDER          # SB3's parameters() order
+    assert list(pol.state_dict()) == sb3_zip.SB3_PARAM_ORDER
+    opt = torch.optim.Adam(pol.parameters(), lr=3e-4, eps=1e-5)
+    x, a = torch.randn(32, 15), torch.randn(32, 4)
+    for _ in range(3):                                     # three genuine Adam steps: non-trivial exp_avg / exp_avg_sq / step
+        opt.zero_grad()
+        mean, value = pol(x)
+        (((mean - a) ** 2).mean() + (value ** 2).mean() + pol.log_std.sum() ** 2).backward()
+        opt.step()
+
+    def pth(o):
+        b = io.BytesIO(); torch.save(o, b); return b.getvalue()
+    p = str(tmp_path / "genuine.zip")
+    with zipfile.ZipFile(p, "w") as z:
+        z.writestr("data", json.dumps({"n_steps": 2048, "batch_size": 64, "n_epochs": 10, "gamma": 0.99, "gae_lambda": 0.95,
+                                       "learning_rate": 0.0003, "num_timesteps": 6144, "_n_updates": 30,
+                                       "policy_class": {":type:": "<class 'abc.ABCMeta'>", ":serialized:": "gAWV..."},
+                                       "clip_range": {":type:": "<class 'function'>", ":serialized:": "gAWV..."}}))
+        z.writestr("policy.pth", pth(pol.state_dict()))
+        z.writestr("policy.optimizer.pth", pth(opt.state_dict()))
+        z.writestr("pytorch_variables.pth", pth(None))
+        z.writestr("_stable_baselines3_version", "2.3.2")
+        z.writestr("system_info.txt", "- OS: Linux\n")
+    got = sb3_zip.import_zip(p)
+    named = {k: v for k, v in pol.state_dict().items()}
+    flat = torch.cat([named[SB3_NAMES[k]].reshape(-1) for k, _ in po.SHAPES])
+    assert torch.equal(got["params"], flat) and got["adam_step"] == 3
+    st = opt.state_dict()["state"]
+    for half, key in ((0, "exp_avg"), (1, "exp_avg_sq")):
+        by_name = {n: st[i][key] for i, n in enumerate(sb3_zip.SB3_PARAM_ORDER)}
+        want = torch.cat([by_name[SB3_NAMES[k]].reshape(-1) for k, _ in po.SHAPES])
+        assert torch.equal(got["adam"][half * POLICY_PARAMS:(half + 1) * POLICY_PARAMS], want)
+    assert got["hyper"]["n_steps"] == 2048 and got["hyper"]["num_timesteps"] == 6144 and "clip_range" not in got["hyper"]
+    mean, value = pol(x)
+    om, ov, _ = po.forward(got["params"], x)
+    assert torch.allclose(om, mean, atol=1e-6) and torch.allclose(ov, value, atol=1e-6)
+    # and back: what export_zip writes loads strictly into the genuine module AND the genuine optimiser, and the next Adam
+    # step of that optimiser equals the oracle's clip-free Adam step on the flat vectors
+    q = str(tmp_path / "back.zip")
+    sb3_zip.export_zip(q, got["params"], got["adam"], got["adam_step"], {"learning_rate": 3e-4})
+    pol2 = _SB3ShapedPolicy()
+    opt2 = torch.optim.Adam(pol2.parameters(), lr=3e-4, eps=1e-5)
+    zf = zipfile.ZipFile(q)
+    pol2.load_state_dict(torch.load(io.BytesIO(zf.read("policy.pth")), weights_only=False), strict=True)
+    opt2.load_state_dict(torch.load(io.BytesIO(zf.read("policy.optimizer.pth")), weights_only=False))
+    for (n1, p1), (n2, p2) in zip(pol.named_parameters(), pol2.named_parameters()):
+        assert n1 == n2 and torch.equal(p1, p2)
+    for o in (opt, opt2):
+        o.zero_grad()
+    for m_ in (pol, pol2):
+        mean, value = m_(x)
+        (((mean - a) ** 2).mean() + (value ** 2).mean()).backward()
+    opt.step(); opt2.step()
+    for p1, p2 in zip(pol.parameters(), pol2.parameters()):
+        assert torch.equal(p1, p2), "the re-imported optimiser state must continue the run bit for bit"
