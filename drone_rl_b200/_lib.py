@@ -112,6 +112,7 @@ _SIGNATURES = {
     "dronecu_ppo_create": (C.c_int, [C.POINTER(PPOConfig), C.c_int, C.POINTER(_P)]),
     "dronecu_ppo_destroy": (C.c_int, [_P]),
     "dronecu_minibatch_permutation": (C.c_int, [C.c_int, C.c_int64, C.c_uint64, C.c_uint64, _P, _P]),
+    "dronecu_minibatch_partition": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_uint64, C.c_uint64, _P, _P]),
     "dronecu_ppo_adv_stats_epoch": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, _P, _P]),
     "dronecu_ppo_adv_stats": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, _P, _P]),
     "dronecu_ppo_grad": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int64, C.c_float, C.c_float, _P, _P, _P]),

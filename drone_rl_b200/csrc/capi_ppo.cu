@@ -28,6 +28,8 @@ struct dronecu_ppo {
   float* partials;   // [2 * n_sm, kGradLen] (the tensor-core kernel writes one vector per warpgroup)
   float* moments;    // [2, kParams]  Adam m | v
   double* adv_partials; // [n_sm * 8, 2]
+  uint32_t* part_hist;  // scratch of dronecu_minibatch_partition (grown on demand)
+  size_t part_hist_len;
   long long* d_step; // device-resident Adam step count (ppo_apply_kernel increments it)
   uint64_t launches;
   float* dbg;        // see dronecu_ppo_debug_buffer
@@ -168,7 +170,7 @@ extern "C" int dronecu_ppo_destroy(dronecu_ppo* p) {
   for (int r = 0; r < kDpMaxWorld; ++r)
     if (p->dp_opened[r]) cudaIpcCloseMemHandle(p->dp.mail[r]);
   cudaFree(p->dp_mail); cudaFree(p->dp.seq); cudaFree(p->dp.status);
-  cudaFree(p->partials); cudaFree(p->moments); cudaFree(p->adv_partials); cudaFree(p->d_step);
+  cudaFree(p->partials); cudaFree(p->moments); cudaFree(p->adv_partials); cudaFree(p->d_step); cudaFree(p->part_hist);
   cudaGetLastError();
   delete p;
   return DRONECU_OK;
@@ -192,10 +194,7 @@ static void philox_host(uint32_t c[4], uint32_t k0, uint32_t k1) {
   }
 }
 
-extern "C" int dronecu_minibatch_permutation(int device, int64_t n, uint64_t seed, uint64_t epoch, int32_t* d_out,
-                                             void* stream) {
-  if (!d_out || n <= 0 || n > ((int64_t)1 << 31) - 1) return fail(DRONECU_ERR_INVALID, "dronecu_minibatch_permutation: bad argument");
-  DeviceGuard guard(device);
+static PermKey perm_key_for(int64_t n, uint64_t seed, uint64_t epoch) {
   PermKey K;
   int bits = 1;
   while (((int64_t)1 << bits) < n) ++bits;
@@ -206,8 +205,45 @@ extern "C" int dronecu_minibatch_permutation(int device, int64_t n, uint64_t see
     philox_host(c, (uint32_t)seed, (uint32_t)(seed >> 32));
     K.mul[r] = c[0] | 1u; K.mul[r + 1] = c[1] | 1u; K.add[r] = c[2]; K.add[r + 1] = c[3];
   }
+  return K;
+}
+
+extern "C" int dronecu_minibatch_permutation(int device, int64_t n, uint64_t seed, uint64_t epoch, int32_t* d_out,
+                                             void* stream) {
+  if (!d_out || n <= 0 || n > ((int64_t)1 << 31) - 1) return fail(DRONECU_ERR_INVALID, "dronecu_minibatch_permutation: bad argument");
+  DeviceGuard guard(device);
+  const PermKey K = perm_key_for(n, seed, epoch);
   perm_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_out, (uint32_t)n, K);
   CUDA_TRY(cudaGetLastError());
+  return DRONECU_OK;
+}
+
+extern "C" int dronecu_minibatch_partition(dronecu_ppo* p, int64_t n, int64_t batch, uint64_t seed, uint64_t epoch, int32_t* d_out,
+                                           void* stream) {
+  if (!p || !d_out || n <= 0 || batch <= 0 || n > ((int64_t)1 << 31) - 1) return fail(DRONECU_ERR_INVALID, "dronecu_minibatch_partition: bad argument");
+  const int64_t n_bins = (n + batch - 1) / batch;
+  if (n_bins > kPartMaxBins) return fail(DRONECU_ERR_UNSUPPORTED, "dronecu_minibatch_partition: more than 64 minibatches per epoch (use dronecu_minibatch_permutation)");
+  DeviceGuard guard(p->device);
+  const PermKey K = perm_key_for(n, seed, epoch);
+  const uint32_t rows_per_warp = 2048;
+  const uint32_t n_chunks = (uint32_t)((n + rows_per_warp - 1) / rows_per_warp);
+  const size_t len = (size_t)n_chunks * (size_t)n_bins;
+  if (len > p->part_hist_len) {            // grown outside any capture: callers warm up before capturing graphs
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    cudaFree(p->part_hist);
+    p->part_hist = nullptr; p->part_hist_len = 0;
+    CUDA_TRY(cudaMalloc(&p->part_hist, sizeof(uint32_t) * len));
+    p->part_hist_len = len;
+  }
+  const unsigned grid = (n_chunks + kPartWarps - 1) / kPartWarps;
+  cudaStream_t st = (cudaStream_t)stream;
+  part_hist_kernel<<<grid, 32 * kPartWarps, 0, st>>>((uint32_t)n, (uint32_t)batch, (uint32_t)n_bins, rows_per_warp, n_chunks, K, p->part_hist);
+  CUDA_TRY(cudaGetLastError());
+  part_scan_kernel<<<1, 1024, 0, st>>>(p->part_hist, (uint32_t)len);
+  CUDA_TRY(cudaGetLastError());
+  part_scatter_kernel<<<grid, 32 * kPartWarps, 0, st>>>((uint32_t)n, (uint32_t)batch, (uint32_t)n_bins, rows_per_warp, n_chunks, K, p->part_hist, d_out);
+  CUDA_TRY(cudaGetLastError());
+  p->launches += 3;
   return DRONECU_OK;
 }
 

@@ -535,4 +535,83 @@ __global__ void perm_kernel(int32_t* __restrict__ out, uint32_t n, const __grid_
   if (i < n) out[i] = (int32_t)perm_apply(i, K, n);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Minibatch PARTITION with sorted rows.  The same keyed bijection f, read the other way round: row r of the buffer belongs
+// to minibatch f(r) / batch (a uniformly random partition into minibatches of exactly `batch` rows, as the slices of a random
+// permutation are), and the index array lists every minibatch's rows in ASCENDING order.  The minibatch gradient is a sum, so
+// the order inside a minibatch is free; ascending rows turn the update kernels' observation gathers from 8 M random 60-byte
+// reads over a 3 GB buffer (one TLB miss per row: the gather issue alone took 4.8k of 17.6k cycles per tile in the in-kernel
+// timeline, profiles/README.md r02) into a forward sweep with ~4-row strides.
+// A stable counting sort by minibatch id, one WARP per chunk of `rows_per_warp` consecutive rows:
+//   part_hist_kernel     H[key][chunk] = rows of the chunk in minibatch `key`
+//   part_scan_kernel     exclusive prefix sum of H in (key, chunk) order, in place (one CTA)
+//   part_scatter_kernel  every warp walks its chunk in row order and writes row r to out[H[key][chunk]++]
+// ---------------------------------------------------------------------------------------------
+constexpr int kPartMaxBins = 64;
+constexpr int kPartWarps = 8;
+
+__device__ __forceinline__ uint32_t part_key(uint32_t r, const PermKey& K, uint32_t n, uint32_t batch) {
+  return perm_apply(r, K, n) / batch;
+}
+
+__global__ void __launch_bounds__(32 * kPartWarps) part_hist_kernel(uint32_t n, uint32_t batch, uint32_t n_bins, uint32_t rows_per_warp,
+                                                                   uint32_t n_chunks, const __grid_constant__ PermKey K, uint32_t* __restrict__ H) {
+  __shared__ uint32_t hist[kPartWarps][kPartMaxBins];
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t chunk = blockIdx.x * kPartWarps + warp;
+  for (uint32_t b = lane; b < n_bins; b += 32) hist[warp][b] = 0;
+  __syncwarp();
+  if (chunk < n_chunks) {
+    const uint32_t lo = chunk * rows_per_warp, hi = min(n, lo + rows_per_warp);
+    for (uint32_t r0 = lo; r0 < hi; r0 += 32) {
+      const uint32_t r = r0 + lane;
+      const bool on = r < hi;
+      const uint32_t key = on ? part_key(r, K, n, batch) : 0xffffffffu;
+      const uint32_t same = __match_any_sync(0xffffffffu, key);
+      if (on && lane == (uint32_t)(__ffs(same) - 1)) hist[warp][key] += __popc(same);
+      __syncwarp();
+    }
+    for (uint32_t b = lane; b < n_bins; b += 32) H[(size_t)b * n_chunks + chunk] = hist[warp][b];
+  }
+}
+
+__global__ void __launch_bounds__(1024) part_scan_kernel(uint32_t* __restrict__ H, uint32_t len) {
+  __shared__ uint32_t part[1024];
+  const uint32_t per = (len + 1023) / 1024, lo = min(len, threadIdx.x * per), hi = min(len, lo + per);
+  uint32_t sum = 0;
+  for (uint32_t i = lo; i < hi; ++i) sum += H[i];
+  part[threadIdx.x] = sum;
+  __syncthreads();
+  for (uint32_t off = 1; off < 1024; off <<= 1) {                   // Hillis-Steele inclusive scan of the 1024 segment sums
+    const uint32_t v = threadIdx.x >= off ? part[threadIdx.x - off] : 0;
+    __syncthreads();
+    part[threadIdx.x] += v;
+    __syncthreads();
+  }
+  uint32_t run = part[threadIdx.x] - sum;                           // exclusive prefix of this thread's segment
+  for (uint32_t i = lo; i < hi; ++i) { const uint32_t v = H[i]; H[i] = run; run += v; }
+}
+
+__global__ void __launch_bounds__(32 * kPartWarps) part_scatter_kernel(uint32_t n, uint32_t batch, uint32_t n_bins, uint32_t rows_per_warp,
+                                                                      uint32_t n_chunks, const __grid_constant__ PermKey K,
+                                                                      const uint32_t* __restrict__ H, int32_t* __restrict__ out) {
+  __shared__ uint32_t base[kPartWarps][kPartMaxBins];
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t chunk = blockIdx.x * kPartWarps + warp;
+  if (chunk >= n_chunks) return;
+  for (uint32_t b = lane; b < n_bins; b += 32) base[warp][b] = H[(size_t)b * n_chunks + chunk];
+  __syncwarp();
+  const uint32_t lo = chunk * rows_per_warp, hi = min(n, lo + rows_per_warp);
+  for (uint32_t r0 = lo; r0 < hi; r0 += 32) {
+    const uint32_t r = r0 + lane;
+    const bool on = r < hi;
+    const uint32_t key = on ? part_key(r, K, n, batch) : 0xffffffffu;
+    const uint32_t same = __match_any_sync(0xffffffffu, key);
+    if (on) out[base[warp][key] + __popc(same & ((1u << lane) - 1u))] = (int32_t)r;
+    __syncwarp();
+    if (on && lane == (uint32_t)(__ffs(same) - 1)) base[warp][key] += __popc(same);
+    __syncwarp();
+  }
+}
+
 }  // namespace dronecu

@@ -14,10 +14,14 @@
 //     is simply [8-feature group][128 samples][16 bytes]: one conflict-free 16-byte store per group (probed on the
 //     B200 for A and B operands, N = 8 / 16 / 72: scratch/mma_probe_bf16.cu);
 //   * 54 KB of shared memory and 136 TMEM columns per tile: THREE compute warpgroups per CTA; the weight-gradient
-//     accumulators (96 columns) are shared by the three and therefore fed by ONE thread (issuer warp 1: steps S4..S6),
-//     in a fixed rotation over the warpgroups, two steps apart (so that they sit in different phases, and so that the
-//     accumulation order -- hence every bit of the result -- does not depend on timing); a second issuer warp serves the
-//     steps that only touch a warpgroup's private columns (S1..S3), walking the same global order;
+//     accumulators (96 columns) are shared by the three and therefore fed by ONE thread (the accumulating issuer: steps
+//     S4..S6) in a FIXED order over the CTA's tiles (so that the accumulation order -- hence every bit of the result --
+//     does not depend on timing), software-pipelined over consecutive tiles: S4(j) S6(j-1) S5(j), so that the issuer
+//     serves another warpgroup while one computes dZ2 / dZ1.  The steps that only touch a warpgroup's private columns
+//     (S1..S3) need no order at all: warp 0 of each warpgroup issues them itself, right after the warpgroup's hand-over
+//     (it would only wait for their completion otherwise).  r02: before, one shared private-step issuer warp walked a
+//     global order, which made every warpgroup's S1 wait for another warpgroup's tanh phase -- 1.9k idle cycles per
+//     tile in the in-kernel timeline;
 //   * tanh'(layer 1) = 1 - H1^2 is stashed per sample as bf16 (2^-9 relative) next to the operands, because H1 itself
 //     survives only as a bf16 operand (1 - h^2 from a rounded h would lose the saturated units); tanh'(layer 2) uses
 //     the fp32 H2 still in TMEM.
@@ -41,7 +45,7 @@ using namespace tcu;            // descriptors, TMEM ld / st helpers, elect_one,
 
 constexpr int kWG3 = 3;
 constexpr int kComputeThreads3 = 128 * kWG3;
-constexpr int kThreads3 = kComputeThreads3 + 64;       // + TWO issuer warps: private steps (S1..S3) | accumulating steps (S4..S6)
+constexpr int kThreads3 = kComputeThreads3 + 32;       // + ONE issuer warp: the accumulating steps (S4..S6); the private steps (S1..S3) are issued by warp 0 of their own warpgroup
 constexpr int kGrp = 128 * 16;                         // one 8-feature group of a bf16 MN-major operand: [128 samples][16 B]
 constexpr int kWgCols = 136;                           // P 64 | Q 64 | G 8
 constexpr int kCP = 0, kCQ = 64, kCG = 128;
@@ -136,88 +140,84 @@ __device__ __forceinline__ void setup3(Smem3& S, const float* __restrict__ theta
   fence_after();
 }
 
-// The issuer warp.  Virtual time v = 0, 1, 2 ...: at v, warpgroup w is served its step v - 2 w (if it has one) -- a
-// fixed rotation, so the three warpgroups run two steps apart and the shared accumulators see the tiles in an order
-// that does not depend on timing.
-template <int ROLE>      // 0: the private steps S1..S3 ; 1: the steps that add into the shared accumulators, S4..S6
-__device__ __forceinline__ void issuer3(Smem3& S, const int64_t n_tiles, const int64_t stride, long long* tlog) {
-  // every descriptor is built once; a K slice, and the warpgroup, only bump the 14-bit start-address field (16-byte units).
-  // The service code exists ONCE (w is a run-time value): unrolled per warpgroup it was 24 KB of straight-line code that
-  // missed the instruction cache on every service (~500 cycles of stall_no_inst between services in the timeline).
-  const uint64_t dW1 = desc_w(smem_addr(S.W1), 16, 0), dW2 = desc_w(smem_addr(S.W2), kHid, 0), dW2T = desc_w(smem_addr(S.W2T), kHid, 0);
-  const uint64_t dW3p = desc_w(smem_addr(S.W3p), kHid, 0), dW3k = desc_w(smem_addr(S.W3k), 8, 0);
-  const uint64_t dXs0 = make_desc(smem_addr(S.XG[0]), kXsLbo, kXsSbo, 0);
-  const uint64_t dA0 = desc_il(smem_addr(S.bufA[0]), 0), dB0 = desc_il(smem_addr(S.bufB[0]), 0), dXn0 = desc_il(smem_addr(S.XN[0][0]), 0);
-  constexpr uint64_t kStrA = (9 * kGrp) >> 4, kStrB = (8 * kGrp) >> 4, kStrXn = (4 * kGrp) >> 4, kParXn = (2 * kGrp) >> 4, kStrXs = 16384 >> 4, kOffG = (8 * kGrp) >> 4;
-  const uint32_t tbase = S.tmem_base;
-  constexpr uint64_t kW = 256 >> 4, kXs = (2 * kXsLbo) >> 4, kIl = 256 >> 4;      // per-slice bumps of the start-address field
-  int steps_[kWG3];
-  int vmax = 0;
+// Descriptors are built once per thread that issues; a K slice, and the warpgroup, only bump the 14-bit start-address
+// field (16-byte units).
+constexpr uint64_t kStrA = (9 * kGrp) >> 4, kStrB = (8 * kGrp) >> 4, kStrXn = (4 * kGrp) >> 4, kParXn = (2 * kGrp) >> 4,
+                   kStrXs = 16384 >> 4, kOffG = (8 * kGrp) >> 4;
+constexpr uint64_t kBumpW = 256 >> 4, kBumpXs = (2 * kXsLbo) >> 4, kBumpIl = 256 >> 4;      // per-slice bumps of the start-address field
+
+// Private steps S1, S2, S3 of warpgroup w: they write only the warpgroup's private TMEM columns, so there is nothing to
+// order against the other warpgroups.  Called by warp 0 of the warpgroup after every thread of it has arrived on `full`.
+// `dA` = descriptor of the step's shared-memory A operand (S1: the X tile) -- unused for S2 / S3 (A in TMEM); `dB` = its weights.
+template <int STEP>
+__device__ __forceinline__ void issue_private(unsigned long long* full, unsigned long long* done, const uint32_t tmem,
+                                              const uint64_t dA, const uint64_t dB, uint32_t& phf) {
+  mbar_wait(full, phf);
+  phf ^= 1;
+  fence_after();
+  if (elect_one()) {
+    if (STEP == 0) {            // S1: D1 = X . W1^T   (tf32, A = X tile in shared memory)
 #pragma unroll
-  for (int w = 0; w < kWG3; ++w) {
-    const int64_t first = (int64_t)blockIdx.x * kWG3 + w;
-    steps_[w] = first < n_tiles ? (int)(6 * ((n_tiles - first + stride - 1) / stride)) : 0;
-    vmax = max(vmax, steps_[w] + 2 * w);
-  }
-  const int steps0 = steps_[0], steps1 = steps_[1], steps2 = steps_[2];
-  uint32_t ph_mask = 0;                                // bit w: parity of warpgroup w's `full` barrier
-  uint32_t stp_pack = 0;                               // 4 bits per warpgroup: its next step (0..5)
-  uint32_t seen3 = 0, seen2 = 0, seen1 = 0;            // has the shared accumulator been written yet
-  uint32_t xn_par = 0;                                 // bit w: which XN buffer warpgroup w's current tile uses
-  int tix = 0;
-  for (int v = 0; v < vmax; ++v) {
-#pragma unroll 1
-    for (int w = 0; w < kWG3; ++w) {
-      // both issuer warps walk the SAME global order (virtual time v, warpgroup w at its step v - 2 w) and each serves
-      // only its own steps: a service can only wait for services that precede it in that order, so the split cannot
-      // deadlock (an independent rotation per role did)
-      const int sidx = v - 2 * w;
-      const int nst = (w == 0) ? steps0 : (w == 1) ? steps1 : steps2;
-      if (sidx < 0 || sidx >= nst) continue;
-      const int step = (stp_pack >> (4 * w)) & 15;
-      stp_pack = (stp_pack & ~(15u << (4 * w))) | ((uint32_t)(step == 5 ? 0 : step + 1) << (4 * w));
-      if ((step >= 3) != (ROLE == 1)) continue;
-      if (w == 0 && (step == 0 || step == 3) && sidx > 2) ++tix;
-      mbar_wait(ROLE ? &S.fullA[w] : &S.full[w], (ph_mask >> w) & 1u);
-      ph_mask ^= 1u << w;
-      fence_after();
-      if (w == 0) TSTAMP(tlog, tix, 2 * step);
-      if (elect_one()) {
-        const uint32_t tmem = tbase + w * kWgCols;
-        const uint64_t uw = (uint64_t)w;
-        if (step == 0) {            // S1: D1 = X . W1^T   (tf32, A = X tile in shared memory)
-          const uint64_t dXs = dXs0 + kStrXs * uw;
+      for (int s = 0; s < 2; ++s) mma_ss(tmem + kCP, dA + kBumpXs * s, dB + kBumpW * s, idesc(128, 64, 0, 0), s > 0);
+    } else if (STEP == 1) {     // S2: D2 = H1 . W2^T  (tf32, A = H1 in TMEM)
 #pragma unroll
-          for (int s = 0; s < 2; ++s) mma_ss(tmem + kCP, dXs + kXs * s, dW1 + kW * s, idesc(128, 64, 0, 0), s > 0);
-        } else if (step == 1) {     // S2: D2 = H1 . W2^T  (tf32, A = H1 in TMEM)
+      for (int s = 0; s < 8; ++s) mma_tf32_ts(tmem + kCQ, tmem + kCP + 8 * s, dB + kBumpW * s, idesc(128, 64, 0, 0), s > 0);
+    } else {                    // S3: D3 = H2 . W3p^T (tf32, A = H2 in TMEM; D3 over the dead H1 in P)
 #pragma unroll
-          for (int s = 0; s < 8; ++s) mma_tf32_ts(tmem + kCQ, tmem + kCP + 8 * s, dW2 + kW * s, idesc(128, 64, 0, 0), s > 0);
-        } else if (step == 2) {     // S3: D3 = H2 . W3p^T (tf32, A = H2 in TMEM; D3 over the dead H1 in P)
-#pragma unroll
-          for (int s = 0; s < 8; ++s) mma_tf32_ts(tmem + kCP, tmem + kCQ + 8 * s, dW3p + kW * s, idesc(128, 16, 0, 0), s > 0);
-        } else if (step == 3) {     // S4: dH2 = G . W3k (tf32, A = G in TMEM, K = 8) ; dW3 += H2^T . G (bf16)
-          mma_tf32_ts(tmem + kCP, tmem + kCG, dW3k, idesc(128, 64, 0, 0), 0);
-          const uint64_t dH = dB0 + kStrB * uw, dG = dA0 + kStrA * uw + kOffG;
-#pragma unroll
-          for (int s = 0; s < 8; ++s) mma_bf16_ss(tbase + kAcc3, dH + kIl * s, dG + kIl * s, idesc_bf16(64, 8, 1, 1), seen3 | (s > 0));
-        } else if (step == 4) {     // S5: dH1 = dZ2 . W2 (tf32, A = dZ2 in TMEM) ; dW2 | db2 += dZ2^T . [H1 | G] (bf16, N = 72)
-#pragma unroll
-          for (int s = 0; s < 8; ++s) mma_tf32_ts(tmem + kCP, tmem + kCQ + 8 * s, dW2T + kW * s, idesc(128, 64, 0, 0), s > 0);
-          const uint64_t dZ = dB0 + kStrB * uw, dHG = dA0 + kStrA * uw;
-#pragma unroll
-          for (int s = 0; s < 8; ++s) mma_bf16_ss(tbase + kAcc2, dZ + kIl * s, dHG + kIl * s, idesc_bf16(64, 72, 1, 1), seen2 | (s > 0));
-        } else {                    // S6: dW1 | db1 += dZ1^T . [X | 1] (bf16, N = 16)
-          const uint64_t dZ = dA0 + kStrA * uw, dX = dXn0 + kStrXn * uw + kParXn * (uint64_t)((xn_par >> w) & 1u);
-#pragma unroll
-          for (int s = 0; s < 8; ++s) mma_bf16_ss(tbase + kAcc1, dZ + kIl * s, dX + kIl * s, idesc_bf16(64, 16, 1, 1), seen1 | (s > 0));
-        }
-        mma_commit(ROLE ? &S.doneA[w] : &S.done[w]);
-      }
-      // the accumulate flags are warp-uniform state: every lane tracks them (only the elected lane issues)
-      if (step == 3) seen3 = 1; else if (step == 4) seen2 = 1; else if (step == 5) { seen1 = 1; xn_par ^= 1u << w; }
-      __syncwarp();
-      if (w == 0) TSTAMP(tlog, tix, 2 * step + 1);
+      for (int s = 0; s < 8; ++s) mma_tf32_ts(tmem + kCP, tmem + kCQ + 8 * s, dB + kBumpW * s, idesc(128, 16, 0, 0), s > 0);
     }
+    mma_commit(done);
+  }
+  __syncwarp();
+}
+
+// The accumulating issuer: S4, S5, S6 of EVERY tile of the CTA, in one fixed order.  The CTA's tiles in global order are
+// j = 3 r + w (round r, warpgroup w); the existing ones are a prefix j = 0 .. n_cta - 1 of that sequence.  Each shared
+// accumulator (dW3 by S4, dW2 | db2 by S5, dW1 | db1 by S6) must receive the tiles in order of j; the services are
+// software-pipelined over consecutive tiles -- S4(0) S5(0) | S4(j) S6(j-1) S5(j) | ... | S6(n-1) -- so that between the two
+// services of one warpgroup that are separated by its dZ2 / dZ1 phases the issuer serves another warpgroup.
+__device__ __forceinline__ void issuer_accum(Smem3& S, const int n_cta, long long* tlog) {
+  const uint64_t dW2T = desc_w(smem_addr(S.W2T), kHid, 0), dW3k = desc_w(smem_addr(S.W3k), 8, 0);
+  const uint64_t dA0 = desc_il(smem_addr(S.bufA[0]), 0), dB0 = desc_il(smem_addr(S.bufB[0]), 0), dXn0 = desc_il(smem_addr(S.XN[0][0]), 0);
+  const uint32_t tbase = S.tmem_base;
+  uint32_t ph_mask = 0;                                // bit w: parity of warpgroup w's `fullA` barrier
+  auto serve = [&](const int j, const int step) __attribute__((always_inline)) {      // step 3, 4, 5 = S4, S5, S6 of tile j
+    const int w = j % kWG3, r = j / kWG3;
+    mbar_wait(&S.fullA[w], (ph_mask >> w) & 1u);
+    ph_mask ^= 1u << w;
+    fence_after();
+    if (w == 0) TSTAMP(tlog, r, 2 * step);
+    if (elect_one()) {
+      const uint32_t tmem = tbase + w * kWgCols;
+      const uint64_t uw = (uint64_t)w;
+      const uint32_t first = j > 0;                    // tile 0 initialises the shared accumulators
+      if (step == 3) {            // S4: dH2 = G . W3k (tf32, A = G in TMEM, K = 8) ; dW3 += H2^T . G (bf16)
+        mma_tf32_ts(tmem + kCP, tmem + kCG, dW3k, idesc(128, 64, 0, 0), 0);
+        const uint64_t dH = dB0 + kStrB * uw, dG = dA0 + kStrA * uw + kOffG;
+#pragma unroll
+        for (int s = 0; s < 8; ++s) mma_bf16_ss(tbase + kAcc3, dH + kBumpIl * s, dG + kBumpIl * s, idesc_bf16(64, 8, 1, 1), first | (s > 0));
+      } else if (step == 4) {     // S5: dH1 = dZ2 . W2 (tf32, A = dZ2 in TMEM) ; dW2 | db2 += dZ2^T . [H1 | G] (bf16, N = 72)
+        const uint64_t dZ = dB0 + kStrB * uw, dHG = dA0 + kStrA * uw;
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {                  // the two products are independent: interleave them in the pipe
+          mma_tf32_ts(tmem + kCP, tmem + kCQ + 8 * s, dW2T + kBumpW * s, idesc(128, 64, 0, 0), s > 0);
+          mma_bf16_ss(tbase + kAcc2, dZ + kBumpIl * s, dHG + kBumpIl * s, idesc_bf16(64, 72, 1, 1), first | (s > 0));
+        }
+      } else {                    // S6: dW1 | db1 += dZ1^T . [X | 1] (bf16, N = 16)
+        const uint64_t dZ = dA0 + kStrA * uw, dX = dXn0 + kStrXn * uw + kParXn * (uint64_t)(r & 1);
+#pragma unroll
+        for (int s = 0; s < 8; ++s) mma_bf16_ss(tbase + kAcc1, dZ + kBumpIl * s, dX + kBumpIl * s, idesc_bf16(64, 16, 1, 1), first | (s > 0));
+      }
+      mma_commit(&S.doneA[w]);
+    }
+    __syncwarp();
+    if (w == 0) TSTAMP(tlog, r, 2 * step + 1);
+  };
+#pragma unroll 1
+  for (int j = 0; j <= n_cta; ++j) {
+    if (j < n_cta) serve(j, 3);
+    if (j > 0) serve(j - 1, 5);
+    if (j < n_cta) serve(j, 4);
   }
 }
 
@@ -240,11 +240,14 @@ __global__ void __launch_bounds__(tcb::kThreads3, 1) ppo_grad_bf16_kernel(const 
 
   if (warp >= 4 * kWG3) {
     long long* tlog = nullptr;
+    auto tiles_of = [&](int w) -> int {
+      const int64_t first = (int64_t)blockIdx.x * kWG3 + w;
+      return first < n_tiles ? (int)((n_tiles - first + stride - 1) / stride) : 0;
+    };
 #if DRONECU_TC_TIMING
     if (A.dbg != nullptr && blockIdx.x == 0 && tw == 0) tlog = reinterpret_cast<long long*>(A.dbg) + 1024;
 #endif
-    if (warp == 4 * kWG3) issuer3<0>(S, n_tiles, stride, tlog);
-    else issuer3<1>(S, n_tiles, stride, tlog);
+    issuer_accum(S, tiles_of(0) + tiles_of(1) + tiles_of(2), tlog);
   } else {
     const int wg = tid >> 7, r = tid & 127, wq = r >> 5;
     float std_inv[kAct], logstd_sum = 0.f;
@@ -268,7 +271,10 @@ __global__ void __launch_bounds__(tcb::kThreads3, 1) ppo_grad_bf16_kernel(const 
     unsigned long long* const fullA = &S.fullA[wg];
     unsigned long long* const done = &S.done[wg];
     unsigned long long* const doneA = &S.doneA[wg];
-    uint32_t phA = 0;
+    uint32_t phA = 0, phf = 0;
+    // descriptors of the private steps (issued by warp 0 of the warpgroup)
+    const uint64_t dXs = make_desc(smem_addr(S.XG[wg]), kXsLbo, kXsSbo, 0), dW1 = desc_w(smem_addr(S.W1), 16, 0);
+    const uint64_t dW2 = desc_w(smem_addr(S.W2), kHid, 0), dW3p = desc_w(smem_addr(S.W3p), kHid, 0);
     const uint32_t tmem = S.tmem_base + wg * kWgCols;
     const uint32_t tL = tmem + ((uint32_t)(wq * 32) << 16);
     uint32_t ph = 0;
@@ -295,9 +301,16 @@ __global__ void __launch_bounds__(tcb::kThreads3, 1) ppo_grad_bf16_kernel(const 
       }
       in.act = make_float4(0.f, 0.f, 0.f, 0.f);
       in.old_logp = in.adv_raw = in.ret = 0.f;
+      // issued HERE, a tile ahead of their use (volatile: as plain loads ptxas sank them to the head phase of the next tile,
+      // where each cost a full DRAM round trip: 3k cycles per tile at the c5 buffer size in the in-kernel timeline)
       if (row >= 0) {
-        if (tw == 0) { in.act = A.actions[row]; in.old_logp = A.old_logp[row]; in.adv_raw = A.adv[row]; }
-        else in.ret = A.ret[row];
+        if (tw == 0) {
+          asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(in.act.x), "=f"(in.act.y), "=f"(in.act.z), "=f"(in.act.w) : "l"(A.actions + row));
+          asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(in.old_logp) : "l"(A.old_logp + row));
+          asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(in.adv_raw) : "l"(A.adv + row));
+        } else {
+          asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(in.ret) : "l"(A.ret + row));
+        }
       }
     };
 
@@ -334,6 +347,7 @@ __global__ void __launch_bounds__(tcb::kThreads3, 1) ppo_grad_bf16_kernel(const 
         }
       }
       hand_over(full);
+      if (wq == 0) issue_private<0>(full, done, tmem, dXs, dW1, phf);
       TSTAMP(tlog, it, 2);
       gather(row_nxt, cur);
       row_cur = row_nxt;
@@ -374,6 +388,7 @@ __global__ void __launch_bounds__(tcb::kThreads3, 1) ppo_grad_bf16_kernel(const 
       }
       wait_st();
       hand_over(full);
+      if (wq == 0) issue_private<1>(full, done, tmem, 0, dW2, phf);
       TSTAMP(tlog, it, 5);
 
       // ---------------- S2 done: H2 = tanh(D2 + b2) -> Q (tf32, A of S3; fp32-accurate copy for tanh'), bufB (bf16) ----------------
@@ -411,6 +426,7 @@ __global__ void __launch_bounds__(tcb::kThreads3, 1) ppo_grad_bf16_kernel(const 
       }
       wait_st();
       hand_over(full);
+      if (wq == 0) issue_private<2>(full, done, tmem, 0, dW3p, phf);
       TSTAMP(tlog, it, 7);
 
       // ---------------- S3 done: head outputs -> loss gradient at the head ----------------

@@ -306,14 +306,22 @@ class PPO:
             self._perm = torch.empty(B, dtype=torch.int32, device=self.device)
         perm = self._perm
         self._info_sum.zero_()
+        n_mb = (B + self.batch_size - 1) // self.batch_size
         for _ in range(self.n_epochs):
-            # SB3: np.random.permutation(B) per epoch; here a keyed bijection evaluated on the device (no sort)
-            _lib.check(self.lib.dronecu_minibatch_permutation(self.device.index, B, self.seed + 1, self._epochs_done,
-                                                              _ptr(perm), _stream_ptr(self.device)), "dronecu_minibatch_permutation")
+            # SB3: np.random.permutation(B) per epoch, minibatch b = slice b of it.  Here a keyed bijection evaluated on the device
+            # (no sort of B keys); with up to 64 minibatches per epoch it is read as "row r belongs to minibatch f(r) // batch" and
+            # every minibatch lists its rows in ascending order (a counting sort by minibatch id): the same uniformly random
+            # partition, and the update kernels sweep the rollout buffer forwards instead of gathering random rows
+            if n_mb <= 64:
+                _lib.check(self.lib.dronecu_minibatch_partition(self._h, B, self.batch_size, self.seed + 1, self._epochs_done,
+                                                                _ptr(perm), _stream_ptr(self.device)), "dronecu_minibatch_partition")
+                self.launches += 3
+            else:
+                _lib.check(self.lib.dronecu_minibatch_permutation(self.device.index, B, self.seed + 1, self._epochs_done,
+                                                                  _ptr(perm), _stream_ptr(self.device)), "dronecu_minibatch_permutation")
+                self.launches += 1
             self._epochs_done += 1
-            self.launches += 1
             # advantage statistics of EVERY minibatch of the epoch: two launches and (data parallel) one all-reduce per epoch
-            n_mb = (B + self.batch_size - 1) // self.batch_size
             ep_stats = None
             if self.normalize_advantage and n_mb <= self._max_mb:
                 if self._ep_stats is None or self._ep_stats.shape[0] != n_mb:

@@ -248,6 +248,16 @@ int dronecu_ppo_destroy(dronecu_ppo* ppo);
  * function is restated in oracle/philox.py (minibatch_permutation); n < 2^31. */
 int dronecu_minibatch_permutation(int device, int64_t n, uint64_t seed, uint64_t epoch, int32_t* d_out, void* stream);
 
+/* The minibatches of one epoch with SORTED rows: the same keyed bijection f read the other way round -- buffer row r belongs
+ * to minibatch f(r) / batch (a uniformly random partition into minibatches of exactly `batch` rows; the last one takes the
+ * remainder) -- and d_out[b * batch .. (b + 1) * batch) lists minibatch b's rows in ascending order (stable counting sort by
+ * minibatch id).  A minibatch gradient is a sum over its rows, so the order inside a minibatch is free; ascending rows make
+ * the update kernels' gathers a forward sweep over the rollout buffer instead of random 60-byte reads.  At most 64
+ * minibatches per epoch (DRONECU_ERR_UNSUPPORTED beyond: use dronecu_minibatch_permutation).  oracle/philox.py:
+ * minibatch_partition. */
+int dronecu_minibatch_partition(dronecu_ppo* ppo, int64_t n, int64_t batch, uint64_t seed, uint64_t epoch, int32_t* d_out,
+                                void* stream);
+
 /* sum, sum of squares and count of the advantages of a minibatch, ACCUMULATED into d_out[3] (float64;
  * zero it first).  Minibatch = rows d_index[0..m) of the flat buffers, or rows first..first+m when
  * d_index is NULL.  (Data-parallel training all-reduces d_out before forming mean / std.) */

@@ -132,3 +132,10 @@ def minibatch_permutation(n: int, seed: int, epoch: int) -> np.ndarray:
         x[todo] = y
         todo[todo] = y >= n
     return x.astype(np.int64)
+
+
+def minibatch_partition(n: int, batch: int, seed: int, epoch: int) -> np.ndarray:
+    """``dronecu_minibatch_partition``: row r belongs to minibatch ``minibatch_permutation(n, seed, epoch)[r] // batch``; the
+    result lists minibatch 0's rows in ascending order, then minibatch 1's, ... (a stable sort by minibatch id)."""
+    key = minibatch_permutation(n, seed, epoch) // batch
+    return np.argsort(key, kind="stable").astype(np.int64)

@@ -19,6 +19,7 @@ __device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a, uint64_t b, uint3
 __device__ __forceinline__ void mma_ss16(uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t acc) {
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" :: "r"(d), "l"(a), "l"(b), "r"(id), "r"(acc) : "memory");
 }
+template <int MODE, int CHAINS>
 __global__ void rate(Cfg c, long long* out) {
   extern __shared__ __align__(1024) unsigned char sm[];
   unsigned char* base = sm + ((1024u - (smem_addr(sm) & 1023u)) & 1023u);
@@ -39,21 +40,20 @@ __global__ void rate(Cfg c, long long* out) {
   if (tid < 32) asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(el));
   if (tid < 32 && el) {
     const uint32_t aA = smem_addr(base), aB = smem_addr(base + 65536);
-    const uint32_t id_ts = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((c.mode == 2 ? 64 : c.N) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    const uint32_t id_ss = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)((c.mode == 2 ? 72 : c.N) >> 3) << 17) | ((uint32_t)(c.M >> 4) << 24);
+    const uint32_t id_ts = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((MODE == 2 ? 64 : c.N) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t id_ss = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)((MODE == 2 ? 72 : c.N) >> 3) << 17) | ((uint32_t)(c.M >> 4) << 24);
     const uint64_t dbw = mkdesc(aB, 128, 2048, 0);                       // K-major weights (B of the TS MMAs)
     const uint64_t dai = mkdesc(aA, 128, 2048, 0), dbi = mkdesc(aB, 128, 2048, 0);   // MN-major interleave operands
     uint32_t parity = 0;
     for (int rep = 0; rep < 4; ++rep) {
       const long long t0 = clock64();
-      for (int s8 = 0; s8 < c.count; s8 += 8) {
+      for (int s8 = 0; s8 < c.count; s8 += 8) {     // count: a multiple of 8 (and of CHAINS where CHAINS == 3: 8 slices x 3 per round)
 #pragma unroll
         for (int sl = 0; sl < 8; ++sl) {
-          const int i = s8 + sl, ch = i % c.chains;
-          const uint32_t acc = i >= c.chains;
-          if (c.mode == 0) mma_ts(tb + 128 * ch, tb + 384 + 8 * sl, dbw + 16 * sl, id_ts, acc);      // up to 3 accumulators of <= 128 columns
-          else if (c.mode == 1) mma_ss16(tb + 128 * ch, dai + 16 * sl, dbi + 16 * sl, id_ss, acc);
-          else { mma_ts(tb, tb + 384 + 8 * sl, dbw + 16 * sl, id_ts, i > 0); mma_ss16(tb + 128, dai + 16 * sl, dbi + 16 * sl, id_ss, i > 0); }
+          const uint32_t acc = s8 > 0;                 // the first round of 8 initialises every accumulator it touches
+          if (MODE == 0) mma_ts(tb + 128 * (sl % CHAINS), tb + 384 + 8 * sl, dbw + 16 * sl, id_ts, acc | (sl >= CHAINS));
+          else if (MODE == 1) mma_ss16(tb + 128 * (sl % CHAINS), dai + 16 * sl, dbi + 16 * sl, id_ss, acc | (sl >= CHAINS));
+          else { mma_ts(tb, tb + 384 + 8 * sl, dbw + 16 * sl, id_ts, acc | (sl > 0)); mma_ss16(tb + 128, dai + 16 * sl, dbi + 16 * sl, id_ss, acc | (sl > 0)); }
         }
       }
       const long long t1 = clock64();
@@ -70,20 +70,22 @@ __global__ void rate(Cfg c, long long* out) {
 }
 int main() {
   Cfg cfgs[] = {
-    {0, 128, 64, 1, 64, "tf32 TS 128x64x8, 1 accumulator"}, {0, 128, 64, 2, 64, "tf32 TS 128x64x8, 2 accumulators"}, {0, 128, 64, 3, 66, "tf32 TS 128x64x8, 3 accumulators"},
+    {0, 128, 64, 1, 64, "tf32 TS 128x64x8, 1 accumulator"}, {0, 128, 64, 2, 64, "tf32 TS 128x64x8, 2 accumulators"}, {0, 128, 64, 3, 64, "tf32 TS 128x64x8, 3 accumulators"},
     {0, 128, 16, 1, 64, "tf32 TS 128x16x8, 1 accumulator"}, {0, 128, 16, 2, 64, "tf32 TS 128x16x8, 2 accumulators"},
     {0, 128, 128, 1, 64, "tf32 TS 128x128x8, 1 accumulator"}, {0, 128, 128, 2, 64, "tf32 TS 128x128x8, 2 accumulators"},
-    {1, 64, 72, 1, 64, "bf16 SS 64x72x16, 1 accumulator"}, {1, 64, 72, 2, 64, "bf16 SS 64x72x16, 2 accumulators"}, {1, 64, 72, 3, 66, "bf16 SS 64x72x16, 3 accumulators"},
+    {1, 64, 72, 1, 64, "bf16 SS 64x72x16, 1 accumulator"}, {1, 64, 72, 2, 64, "bf16 SS 64x72x16, 2 accumulators"}, {1, 64, 72, 3, 64, "bf16 SS 64x72x16, 3 accumulators"},
     {1, 64, 16, 1, 64, "bf16 SS 64x16x16, 1 accumulator"}, {1, 64, 16, 2, 64, "bf16 SS 64x16x16, 2 accumulators"},
     {1, 64, 8, 1, 64, "bf16 SS 64x8x16, 1 accumulator"}, {1, 64, 8, 2, 64, "bf16 SS 64x8x16, 2 accumulators"},
     {1, 128, 96, 1, 64, "bf16 SS 128x96x16, 1 accumulator (stacked dZ2|dZ1)"}, {1, 128, 96, 2, 64, "bf16 SS 128x96x16, 2 accumulators"},
     {1, 128, 80, 1, 64, "bf16 SS 128x80x16, 1 accumulator"}, {1, 128, 128, 1, 64, "bf16 SS 128x128x16, 1 accumulator"},
     {2, 64, 72, 1, 64, "S5 mix: TS 128x64x8 -> P alternating with SS 64x72x16 -> acc (64 of each)"},
   };
-  cudaFuncSetAttribute(rate, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072 + 1024);
   long long* d; cudaMalloc(&d, 64);
   for (Cfg c : cfgs) {
-    rate<<<1, 128, 131072 + 1024>>>(c, d);
+    auto k = c.mode == 2 ? rate<2, 1> : c.mode == 0 ? (c.chains == 1 ? rate<0, 1> : c.chains == 2 ? rate<0, 2> : rate<0, 3>)
+                                                      : (c.chains == 1 ? rate<1, 1> : c.chains == 2 ? rate<1, 2> : rate<1, 3>);
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072 + 1024);
+    k<<<1, 128, 131072 + 1024>>>(c, d);
     cudaError_t e = cudaDeviceSynchronize();
     long long h[8]; cudaMemcpy(h, d, 64, cudaMemcpyDeviceToHost);
     const int n = c.mode == 2 ? 2 * c.count : c.count;

@@ -3,9 +3,13 @@ sys.path.insert(0, '.')
 from drone_rl_b200 import _lib
 from drone_rl_b200.ppo import PPO
 np.set_printoptions(linewidth=220)
-tiles_per_wg = 8
+# usage: tc_timing4.py [tiles_per_wg] [n_envs] [K]   (defaults: a small L2-resident buffer; pass 1048576 32 for the c5 shape,
+# where the minibatch rows are scattered over a 3 GB rollout buffer)
+tiles_per_wg = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 m = 128 * 3 * 74 * tiles_per_wg
-n = 8192; K = (m + n - 1) // n + 1
+n = int(sys.argv[2]) if len(sys.argv) > 2 else 8192
+K = int(sys.argv[3]) if len(sys.argv) > 3 else (m + n - 1) // n + 1
+assert m <= n * K
 model = PPO(n, n_steps=K, update_precision="bf16"); model.collect_rollouts()
 P = lambda t: None if t is None else C.c_void_p(t.data_ptr())
 dbg = torch.zeros(1 << 20, device='cuda'); _lib.check(model.lib.dronecu_ppo_debug_buffer(model._h, P(dbg)))

@@ -366,3 +366,29 @@ def test_epoch_advantage_statistics(drl):
         np.testing.assert_allclose(got[:2], [a.sum(), (a * a).sum()], rtol=1e-12)
         np.testing.assert_allclose(got[:2], one[:2].cpu().numpy(), rtol=1e-13)
     model.close()
+
+
+@pytest.mark.parametrize("n,batch", [(64, 64), (2048, 64), (4097, 1000), (65536 * 32, 65536 * 8), (3_000_001, 46_876), (1 << 20, 1 << 14)])
+def test_minibatch_partition_matches_oracle(drl, n, batch):
+    """dronecu_minibatch_partition: the uniformly random partition "row r -> minibatch f(r) // batch" with every minibatch's
+    rows in ascending order == a stable sort of the oracle's keyed permutation by minibatch id; a permutation of 0..n-1."""
+    import ctypes as C
+    from drone_rl_b200 import _lib
+    lib = _lib.load()
+    cfg = _lib.PPOConfig()
+    lib.dronecu_ppo_config_default(C.byref(cfg))
+    h = C.c_void_p()
+    _lib.check(lib.dronecu_ppo_create(C.byref(cfg), 0, C.byref(h)))
+    out = torch.empty(n, dtype=torch.int32, device="cuda")
+    n_mb = (n + batch - 1) // batch
+    for epoch in (0, 7):
+        _lib.check(lib.dronecu_minibatch_partition(h, n, batch, 4242, epoch, C.c_void_p(out.data_ptr()), None))
+        torch.cuda.synchronize()
+        got = out.cpu().numpy().astype(np.int64)
+        assert np.array_equal(got, philox.minibatch_partition(n, batch, 4242, epoch))
+        assert np.array_equal(np.sort(got), np.arange(n))
+        for b in range(min(n_mb, 8)):
+            seg = got[b * batch:(b + 1) * batch]
+            assert (np.diff(seg) > 0).all() and len(seg) == min(batch, n - b * batch)
+    assert lib.dronecu_minibatch_partition(h, 6500, 100, 1, 0, C.c_void_p(out.data_ptr()), None) != 0      # 65 minibatches: unsupported
+    lib.dronecu_ppo_destroy(h)
