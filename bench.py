@@ -103,6 +103,8 @@ class ClockSampler:
     def __init__(self, index):
         self.samples, self.reasons, self.ok = [], set(), False
         self._stop = threading.Event()
+        if os.environ.get("DRONECU_NO_CLOCKS") == "1":          # debugging aid: no sampler thread
+            return
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -592,10 +594,16 @@ def ppo_variant(ctx, args, wl, n, K, minibatches, epochs, rollout_precision, upd
                 rollout_precision=rollout_precision, update_precision=update_precision, dp_backend=args.dp_backend)
     full = wl in ("c5", "c1")
 
+    debug = os.environ.get("DRONECU_BENCH_DEBUG") == "1"
+
     def one_step():
         model.collect_rollouts()
         if full:
             model.train()
+            if debug:
+                print("[debug]", rollout_precision, update_precision, "param checksum %.15g" % float(model.params.double().sum()),
+                      {k.split("/")[1]: v for k, v in model.logger_values.items() if k.split("/")[1] in ("policy_gradient_loss", "value_loss", "std")},
+                      file=sys.stderr, flush=True)
 
     for _ in range(warmup):
         one_step()

@@ -38,6 +38,14 @@
 #define DRONECU_TF32_ROUND 1
 #endif
 
+// A/B knobs of the accumulating issuer (r02 race hunt): software-pipelined service order, interleaved S5 products
+#ifndef DRONECU_ACC_PIPELINED
+#define DRONECU_ACC_PIPELINED 1
+#endif
+#ifndef DRONECU_S5_INTERLEAVE
+#define DRONECU_S5_INTERLEAVE 1
+#endif
+
 namespace dronecu {
 namespace tcb {
 
@@ -58,7 +66,7 @@ struct alignas(1024) Smem3 {
   unsigned char bufA[kWG3][9 * kGrp];    // bf16: groups 0..7 = H1, later dZ1; group 8 = G (g3[0..3] | live | 0 0 0)
   unsigned char bufB[kWG3][8 * kGrp];    // bf16: H2, later dZ2
   unsigned char XN[kWG3][2][2 * kGrp];   // bf16: X (x0..x14, 1): B of S6; double-buffered (tile parity) so that the next tile is staged while S6 runs
-  unsigned char XG[kWG3][16384];         // tf32 X tile (A of S1, 9216 B), then bf16(1 - H1^2), 128 B per sample
+  unsigned char XG[kWG3][16384];         // bf16(1 - H1^2), 128 B per sample (the tanh' stash; r01 also staged the tf32 X tile here)
   float W1[kHid * 16];
   float W2[kHid * kHid];
   float W2T[kHid * kHid];
@@ -198,11 +206,18 @@ __device__ __forceinline__ void issuer_accum(Smem3& S, const int n_cta, long lon
         for (int s = 0; s < 8; ++s) mma_bf16_ss(tbase + kAcc3, dH + kBumpIl * s, dG + kBumpIl * s, idesc_bf16(64, 8, 1, 1), first | (s > 0));
       } else if (step == 4) {     // S5: dH1 = dZ2 . W2 (tf32, A = dZ2 in TMEM) ; dW2 | db2 += dZ2^T . [H1 | G] (bf16, N = 72)
         const uint64_t dZ = dB0 + kStrB * uw, dHG = dA0 + kStrA * uw;
+#if DRONECU_S5_INTERLEAVE
 #pragma unroll
         for (int s = 0; s < 8; ++s) {                  // the two products are independent: interleave them in the pipe
           mma_tf32_ts(tmem + kCP, tmem + kCQ + 8 * s, dW2T + kBumpW * s, idesc(128, 64, 0, 0), s > 0);
           mma_bf16_ss(tbase + kAcc2, dZ + kBumpIl * s, dHG + kBumpIl * s, idesc_bf16(64, 72, 1, 1), first | (s > 0));
         }
+#else
+#pragma unroll
+        for (int s = 0; s < 8; ++s) mma_tf32_ts(tmem + kCP, tmem + kCQ + 8 * s, dW2T + kBumpW * s, idesc(128, 64, 0, 0), s > 0);
+#pragma unroll
+        for (int s = 0; s < 8; ++s) mma_bf16_ss(tbase + kAcc2, dZ + kBumpIl * s, dHG + kBumpIl * s, idesc_bf16(64, 72, 1, 1), first | (s > 0));
+#endif
       } else {                    // S6: dW1 | db1 += dZ1^T . [X | 1] (bf16, N = 16)
         const uint64_t dZ = dA0 + kStrA * uw, dX = dXn0 + kStrXn * uw + kParXn * (uint64_t)(r & 1);
 #pragma unroll
@@ -213,12 +228,21 @@ __device__ __forceinline__ void issuer_accum(Smem3& S, const int n_cta, long lon
     __syncwarp();
     if (w == 0) TSTAMP(tlog, r, 2 * step + 1);
   };
+#if DRONECU_ACC_PIPELINED
 #pragma unroll 1
   for (int j = 0; j <= n_cta; ++j) {
     if (j < n_cta) serve(j, 3);
     if (j > 0) serve(j - 1, 5);
     if (j < n_cta) serve(j, 4);
   }
+#else
+#pragma unroll 1
+  for (int j = 0; j < n_cta; ++j) {
+    serve(j, 3);
+    serve(j, 4);
+    serve(j, 5);
+  }
+#endif
 }
 
 }  // namespace tcb
@@ -264,7 +288,11 @@ __global__ void __launch_bounds__(tcb::kThreads3, 1) ppo_grad_bf16_kernel(const 
     unsigned char* const rowA = S.bufA[wg] + r * 16;       // + g * kGrp: this sample's 16 bytes of feature group g
     unsigned char* const rowB = S.bufB[wg] + r * 16;
     unsigned char* const XN0 = S.XN[wg][0];
-    unsigned char* const XS = S.XG[wg];
+    // tf32 X tile (A operand of S1, 9216 B): staged over the DEAD bufB of the previous tile (dZ2: read only by the tensor core,
+    // S5 has completed) -- no thread ever reads that region.  r01 staged it over the tanh' stash, whose rows other warps of the
+    // warpgroup still read in their dZ1 phase: with the private steps issued by warp 0 that aliasing produced one garbage
+    // 8-feature block of dW1 per ~1500 launches at the c5 size (scratch/stress_determinism.py).
+    unsigned char* const XS = S.bufB[wg];
     unsigned char* const rowG1 = S.XG[wg] + r * 128;       // 8 chunks of 16 B, chunk c at ((c ^ (r & 7)) << 4)
     const int sw = r & 7;
     unsigned long long* const full = &S.full[wg];
@@ -273,7 +301,7 @@ __global__ void __launch_bounds__(tcb::kThreads3, 1) ppo_grad_bf16_kernel(const 
     unsigned long long* const doneA = &S.doneA[wg];
     uint32_t phA = 0, phf = 0;
     // descriptors of the private steps (issued by warp 0 of the warpgroup)
-    const uint64_t dXs = make_desc(smem_addr(S.XG[wg]), kXsLbo, kXsSbo, 0), dW1 = desc_w(smem_addr(S.W1), 16, 0);
+    const uint64_t dXs = make_desc(smem_addr(S.bufB[wg]), kXsLbo, kXsSbo, 0), dW1 = desc_w(smem_addr(S.W1), 16, 0);
     const uint64_t dW2 = desc_w(smem_addr(S.W2), kHid, 0), dW3p = desc_w(smem_addr(S.W3p), kHid, 0);
     const uint32_t tmem = S.tmem_base + wg * kWgCols;
     const uint32_t tL = tmem + ((uint32_t)(wq * 32) << 16);
@@ -329,8 +357,7 @@ __global__ void __launch_bounds__(tcb::kThreads3, 1) ppo_grad_bf16_kernel(const 
       const float4 act = cur.act;
       const float old_logp = cur.old_logp, adv_raw = cur.adv_raw, ret = cur.ret;
       // The next tile is staged and handed over (S1) WITHOUT waiting for S6 of the previous one: X goes to the other XN
-      // buffer and to XS, neither of which S6 reads.  XS aliases this warp's rows of the tanh' stash: every lane of the
-      // warp has read its row (before handing S6 over) -- make that warp-wide.
+      // buffer and to XS (over the dead bufB), neither of which S6 reads.
       __syncwarp();
       TSTAMP(tlog, it, 1);
       // ---------------- X -> shared memory: tf32 [samples x 16] (A of S1) and bf16 MN-major (B of S6) ----------------

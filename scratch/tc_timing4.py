@@ -5,15 +5,19 @@ from drone_rl_b200.ppo import PPO
 np.set_printoptions(linewidth=220)
 # usage: tc_timing4.py [tiles_per_wg] [n_envs] [K]   (defaults: a small L2-resident buffer; pass 1048576 32 for the c5 shape,
 # where the minibatch rows are scattered over a 3 GB rollout buffer)
-tiles_per_wg = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+argv = [a for a in sys.argv if not a.startswith('--')]
+tiles_per_wg = int(argv[1]) if len(argv) > 1 else 8
 m = 128 * 3 * 74 * tiles_per_wg
-n = int(sys.argv[2]) if len(sys.argv) > 2 else 8192
-K = int(sys.argv[3]) if len(sys.argv) > 3 else (m + n - 1) // n + 1
+n = int(argv[2]) if len(argv) > 2 else 8192
+K = int(argv[3]) if len(argv) > 3 else (m + n - 1) // n + 1
 assert m <= n * K
 model = PPO(n, n_steps=K, update_precision="bf16"); model.collect_rollouts()
 P = lambda t: None if t is None else C.c_void_p(t.data_ptr())
 dbg = torch.zeros(1 << 20, device='cuda'); _lib.check(model.lib.dronecu_ppo_debug_buffer(model._h, P(dbg)))
-b = model.buf; idx = torch.randperm(K * n, device='cuda')[:m].to(torch.int32)
+b = model.buf; idx = torch.randperm(K * n, device='cuda')[:m]
+if '--random' not in sys.argv:
+    idx = idx.sort().values          # what dronecu_minibatch_partition produces: ascending rows inside a minibatch
+idx = idx.to(torch.int32)
 for rep in range(2):
     dbg.zero_(); model._adv_stats.zero_()
     _lib.check(model.lib.dronecu_ppo_adv_stats(model._h, P(b.adv), P(idx), 0, m, P(model._adv_stats), None))
@@ -39,7 +43,7 @@ for it in (3, 4):
 ev = []
 for w in range(3):
     a = t[1024 + 256 * w: 1024 + 256 * w + 256].reshape(16, 16)
-    for it in range(tiles_per_wg):
+    for it in range(min(tiles_per_wg, 16)):
         for st in range(6):
             ev.append((a[it, 2 * st] - t0, a[it, 2 * st + 1] - t0, w, it, st))
 ev.sort()

@@ -221,3 +221,33 @@ def test_tc_gradient_is_race_free_under_repetition(drl, mode):
     for _ in range(40):
         assert np.array_equal(_grad(model, idx, m, tc=mode), first)
     model.close()
+
+
+def test_tc_gradient_is_race_free_at_the_c5_scale(drl):
+    """1500 launches of the bf16 gradient kernel on ONE 8.4M-sample minibatch of a 1M-env x 32-step buffer (configs[4]) must be
+    bit-identical.  At this size DRAM latency jitters the warps far more than in the small repetition test above: an aliasing
+    race between the staged X tile and another warp's tanh' stash (r02) showed up here once per ~1500 launches and never at
+    the small sizes (scratch/stress_determinism.py found it)."""
+    import ctypes as C
+    from drone_rl_b200 import _lib
+    from drone_rl_b200.ppo import PPO
+    n, K, mb = 1 << 20, 32, 4
+    model = PPO(n, n_steps=K, batch_size=n * K // mb, rollout_precision="tf32", update_precision="bf16")
+    model.collect_rollouts()
+    P = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+    b, B, m = model.buf, n * K, n * K // mb
+    perm = torch.empty(B, dtype=torch.int32, device="cuda")
+    _lib.check(model.lib.dronecu_minibatch_partition(model._h, B, m, 1, 0, P(perm), None))
+    stats = torch.zeros(mb, 3, dtype=torch.float64, device="cuda")
+    _lib.check(model.lib.dronecu_ppo_adv_stats_epoch(model._h, P(b.adv), P(perm), B, m, P(stats), None))
+    g, ref, bad = torch.zeros(_lib.GRAD_LEN, device="cuda"), None, 0
+    for i in range(1500):
+        _lib.check(model.lib.dronecu_ppo_grad_bf16(model._h, P(model.params), P(b.obs), P(b.actions), P(b.logp), P(b.adv), P(b.ret),
+                                                   P(perm[:m]), 0, m, 0.0, 1.0, P(stats[0]), P(g), None))
+        if ref is None:
+            ref = g.clone()
+            assert bool(torch.isfinite(ref).all())
+        else:
+            bad += int(not torch.equal(g, ref))
+    assert bad == 0, f"{bad} of 1500 launches differ"
+    model.close()
