@@ -319,18 +319,24 @@ __global__ void __launch_bounds__(tcb::kThreads3, 1) ppo_grad_bf16_kernel(const 
       asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(A.index + pos));
       return v;
     };
-    auto gather = [&](int row32, RowIn& in) {
+    // The next tile's rows are fetched a tile ahead, in FOUR parts spread over the current tile (after the S1 / S2 / S3 / S4
+    // hand-overs, where the warp would otherwise only wait for the tensor core): issued in one burst, the ~550 sectors of a
+    // tile overflow the SM's outstanding-miss capacity and the load ISSUE stalled for 3-4k of 15k cycles per tile (in-kernel
+    // timeline at the c5 size, profiles/r02_grad_timeline_sorted_rows_c5_size.txt).
+    auto gather_rows = [&](int row32, RowIn& in, const int p0) {      // observation rows: 4 of the 16 two-row loads
       const int col = min(lane & 15, kObs - 1), half = lane >> 4;
-      const int64_t row = row32;
 #pragma unroll
-      for (int p = 0; p < 16; ++p) {
+      for (int q = 0; q < 4; ++q) {
+        const int p = p0 + q;
         const int rr = max(__shfl_sync(0xffffffffu, row32, 2 * p + half), 0);
         asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(in.xe[p]) : "l"(A.obs + (int64_t)rr * kObs + col));
       }
+    };
+    auto gather_scalars = [&](int row32, RowIn& in) {
+      const int64_t row = row32;
       in.act = make_float4(0.f, 0.f, 0.f, 0.f);
       in.old_logp = in.adv_raw = in.ret = 0.f;
-      // issued HERE, a tile ahead of their use (volatile: as plain loads ptxas sank them to the head phase of the next tile,
-      // where each cost a full DRAM round trip: 3k cycles per tile at the c5 buffer size in the in-kernel timeline)
+      // volatile: as plain loads ptxas sank them to the head phase of the next tile, where each cost a full DRAM round trip
       if (row >= 0) {
         if (tw == 0) {
           asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(in.act.x), "=f"(in.act.y), "=f"(in.act.z), "=f"(in.act.w) : "l"(A.actions + row));
@@ -349,7 +355,8 @@ __global__ void __launch_bounds__(tcb::kThreads3, 1) ppo_grad_bf16_kernel(const 
     int64_t tile = (int64_t)blockIdx.x * kWG3 + wg;
     int row_cur = row_of(tile), row_nxt = row_of(tile + stride);
     RowIn cur;
-    gather(row_cur, cur);
+    for (int p0 = 0; p0 < 16; p0 += 4) gather_rows(row_cur, cur, p0);
+    gather_scalars(row_cur, cur);
     int it = 0;
     for (; tile < n_tiles; tile += stride, ++it) {
       const bool live = row_cur >= 0;
@@ -376,9 +383,8 @@ __global__ void __launch_bounds__(tcb::kThreads3, 1) ppo_grad_bf16_kernel(const 
       hand_over(full);
       if (wq == 0) issue_private<0>(full, done, tmem, dXs, dW1, phf);
       TSTAMP(tlog, it, 2);
-      gather(row_nxt, cur);
-      row_cur = row_nxt;
-      row_nxt = row_of(tile + 2 * stride);
+      const int row_nn = row_of(tile + 2 * stride);       // the tile after the next: its row numbers are needed a tile from now
+      gather_rows(row_nxt, cur, 0);
       TSTAMP(tlog, it, 3);
       if (it > 0) { mbar_wait(doneA, phA); phA ^= 1; fence_after(); }    // S6 of the previous tile has read bufA (H1 goes there next)
 
@@ -416,6 +422,7 @@ __global__ void __launch_bounds__(tcb::kThreads3, 1) ppo_grad_bf16_kernel(const 
       wait_st();
       hand_over(full);
       if (wq == 0) issue_private<1>(full, done, tmem, 0, dW2, phf);
+      gather_rows(row_nxt, cur, 4);
       TSTAMP(tlog, it, 5);
 
       // ---------------- S2 done: H2 = tanh(D2 + b2) -> Q (tf32, A of S3; fp32-accurate copy for tanh'), bufB (bf16) ----------------
@@ -454,6 +461,7 @@ __global__ void __launch_bounds__(tcb::kThreads3, 1) ppo_grad_bf16_kernel(const 
       wait_st();
       hand_over(full);
       if (wq == 0) issue_private<2>(full, done, tmem, 0, dW3p, phf);
+      gather_rows(row_nxt, cur, 8);
       TSTAMP(tlog, it, 7);
 
       // ---------------- S3 done: head outputs -> loss gradient at the head ----------------
@@ -504,6 +512,8 @@ __global__ void __launch_bounds__(tcb::kThreads3, 1) ppo_grad_bf16_kernel(const 
       }
       wait_st();
       hand_over(fullA);
+      gather_rows(row_nxt, cur, 12);
+      gather_scalars(row_nxt, cur);                        // this tile's act / old_logp / adv / ret live in locals since the top
       TSTAMP(tlog, it, 9);
 
       // ---------------- S4 done: dZ2 = dH2 * (1 - H2^2) -> Q (tf32, A of S5), bufB (bf16, A of S5's wgrad) ----------------
@@ -561,6 +571,8 @@ __global__ void __launch_bounds__(tcb::kThreads3, 1) ppo_grad_bf16_kernel(const 
         }
       }
       hand_over(fullA);                          // S6; awaited at the top of the next tile / after the loop
+      row_cur = row_nxt;
+      row_nxt = row_nn;
       TSTAMP(tlog, it, 13);
     }
     if (it > 0) { mbar_wait(doneA, phA); phA ^= 1; }
