@@ -421,8 +421,10 @@ __global__ void __launch_bounds__(tcb::kThreads3, 1) ppo_grad_bf16_kernel(const 
       }
       wait_st();
       hand_over(full);
+      // warp 0 issues this step's MMAs (it can sit in the issue for ~1k cycles when the tensor pipe's queue is full): it takes
+      // its second and third part of the gather after the S4 / S5 hand-overs instead, where the accumulating issuer issues
       if (wq == 0) issue_private<1>(full, done, tmem, 0, dW2, phf);
-      gather_rows(row_nxt, cur, 4);
+      else gather_rows(row_nxt, cur, 4);
       TSTAMP(tlog, it, 5);
 
       // ---------------- S2 done: H2 = tanh(D2 + b2) -> Q (tf32, A of S3; fp32-accurate copy for tanh'), bufB (bf16) ----------------
@@ -461,7 +463,7 @@ __global__ void __launch_bounds__(tcb::kThreads3, 1) ppo_grad_bf16_kernel(const 
       wait_st();
       hand_over(full);
       if (wq == 0) issue_private<2>(full, done, tmem, 0, dW3p, phf);
-      gather_rows(row_nxt, cur, 8);
+      else gather_rows(row_nxt, cur, 8);
       TSTAMP(tlog, it, 7);
 
       // ---------------- S3 done: head outputs -> loss gradient at the head ----------------
@@ -513,6 +515,7 @@ __global__ void __launch_bounds__(tcb::kThreads3, 1) ppo_grad_bf16_kernel(const 
       wait_st();
       hand_over(fullA);
       gather_rows(row_nxt, cur, 12);
+      if (wq == 0) gather_rows(row_nxt, cur, 4);
       gather_scalars(row_nxt, cur);                        // this tile's act / old_logp / adv / ret live in locals since the top
       TSTAMP(tlog, it, 9);
 
@@ -542,6 +545,7 @@ __global__ void __launch_bounds__(tcb::kThreads3, 1) ppo_grad_bf16_kernel(const 
       }
       wait_st();
       hand_over(fullA);
+      if (wq == 0) gather_rows(row_nxt, cur, 8);
       TSTAMP(tlog, it, 11);
 
       // ---------------- S5 done: dZ1 = dH1 * (1 - H1^2) -> bufA (bf16, A of S6) ----------------
