@@ -53,7 +53,11 @@ using namespace tcu;            // descriptors, TMEM ld / st helpers, elect_one,
 
 constexpr int kWG3 = 3;
 constexpr int kComputeThreads3 = 128 * kWG3;
-constexpr int kThreads3 = kComputeThreads3 + 32;       // + ONE issuer warp: the accumulating steps (S4..S6); the private steps (S1..S3) are issued by warp 0 of their own warpgroup
+#ifndef DRONECU_PRIVATE_ISSUER_WARPS
+#define DRONECU_PRIVATE_ISSUER_WARPS 1   // 1: one private-step issuer warp per warpgroup (512 threads); 0: warp 0 of the warpgroup issues them (416 threads)
+#endif
+constexpr int kIssuerWarps3 = DRONECU_PRIVATE_ISSUER_WARPS ? kWG3 + 1 : 1;
+constexpr int kThreads3 = kComputeThreads3 + 32 * kIssuerWarps3;   // compute warpgroups + issuer warps (the LAST one is the accumulating issuer: S4..S6)
 constexpr int kGrp = 128 * 16;                         // one 8-feature group of a bf16 MN-major operand: [128 samples][16 B]
 constexpr int kWgCols = 136;                           // P 64 | Q 64 | G 8
 constexpr int kCP = 0, kCQ = 64, kCG = 128;
@@ -268,10 +272,27 @@ __global__ void __launch_bounds__(tcb::kThreads3, 1) ppo_grad_bf16_kernel(const 
       const int64_t first = (int64_t)blockIdx.x * kWG3 + w;
       return first < n_tiles ? (int)((n_tiles - first + stride - 1) / stride) : 0;
     };
+    const int iw = warp - 4 * kWG3;
+    if (iw == kIssuerWarps3 - 1) {
 #if DRONECU_TC_TIMING
-    if (A.dbg != nullptr && blockIdx.x == 0 && tw == 0) tlog = reinterpret_cast<long long*>(A.dbg) + 1024;
+      if (A.dbg != nullptr && blockIdx.x == 0 && tw == 0) tlog = reinterpret_cast<long long*>(A.dbg) + 1024;
 #endif
-    issuer_accum(S, tiles_of(0) + tiles_of(1) + tiles_of(2), tlog);
+      issuer_accum(S, tiles_of(0) + tiles_of(1) + tiles_of(2), tlog);
+    } else {
+      // private-step issuer of warpgroup iw: S1, S2, S3 of each of its tiles, in the warpgroup's own order -- these steps write only
+      // the warpgroup's private TMEM columns, so there is nothing to order against the other warpgroups
+      const uint32_t tmem_w = S.tmem_base + iw * kWgCols;
+      const uint64_t dXs = make_desc(smem_addr(S.bufB[iw]), kXsLbo, kXsSbo, 0), dW1 = desc_w(smem_addr(S.W1), 16, 0);
+      const uint64_t dW2 = desc_w(smem_addr(S.W2), kHid, 0), dW3p = desc_w(smem_addr(S.W3p), kHid, 0);
+      uint32_t phf = 0;
+      const int my_tiles = tiles_of(iw);
+#pragma unroll 1
+      for (int t = 0; t < my_tiles; ++t) {
+        issue_private<0>(&S.full[iw], &S.done[iw], tmem_w, dXs, dW1, phf);
+        issue_private<1>(&S.full[iw], &S.done[iw], tmem_w, 0, dW2, phf);
+        issue_private<2>(&S.full[iw], &S.done[iw], tmem_w, 0, dW3p, phf);
+      }
+    }
   } else {
     const int wg = tid >> 7, r = tid & 127, wq = r >> 5;
     float std_inv[kAct], logstd_sum = 0.f;
@@ -299,10 +320,13 @@ __global__ void __launch_bounds__(tcb::kThreads3, 1) ppo_grad_bf16_kernel(const 
     unsigned long long* const fullA = &S.fullA[wg];
     unsigned long long* const done = &S.done[wg];
     unsigned long long* const doneA = &S.doneA[wg];
-    uint32_t phA = 0, phf = 0;
+    uint32_t phA = 0;
+#if !DRONECU_PRIVATE_ISSUER_WARPS
+    uint32_t phf = 0;
     // descriptors of the private steps (issued by warp 0 of the warpgroup)
     const uint64_t dXs = make_desc(smem_addr(S.bufB[wg]), kXsLbo, kXsSbo, 0), dW1 = desc_w(smem_addr(S.W1), 16, 0);
     const uint64_t dW2 = desc_w(smem_addr(S.W2), kHid, 0), dW3p = desc_w(smem_addr(S.W3p), kHid, 0);
+#endif
     const uint32_t tmem = S.tmem_base + wg * kWgCols;
     const uint32_t tL = tmem + ((uint32_t)(wq * 32) << 16);
     uint32_t ph = 0;
@@ -381,7 +405,9 @@ __global__ void __launch_bounds__(tcb::kThreads3, 1) ppo_grad_bf16_kernel(const 
         }
       }
       hand_over(full);
+#if !DRONECU_PRIVATE_ISSUER_WARPS
       if (wq == 0) issue_private<0>(full, done, tmem, dXs, dW1, phf);
+#endif
       TSTAMP(tlog, it, 2);
       const int row_nn = row_of(tile + 2 * stride);       // the tile after the next: its row numbers are needed a tile from now
       gather_rows(row_nxt, cur, 0);
@@ -423,8 +449,12 @@ __global__ void __launch_bounds__(tcb::kThreads3, 1) ppo_grad_bf16_kernel(const 
       hand_over(full);
       // warp 0 issues this step's MMAs (it can sit in the issue for ~1k cycles when the tensor pipe's queue is full): it takes
       // its second and third part of the gather after the S4 / S5 hand-overs instead, where the accumulating issuer issues
+#if DRONECU_PRIVATE_ISSUER_WARPS
+      gather_rows(row_nxt, cur, 4);
+#else
       if (wq == 0) issue_private<1>(full, done, tmem, 0, dW2, phf);
       else gather_rows(row_nxt, cur, 4);
+#endif
       TSTAMP(tlog, it, 5);
 
       // ---------------- S2 done: H2 = tanh(D2 + b2) -> Q (tf32, A of S3; fp32-accurate copy for tanh'), bufB (bf16) ----------------
@@ -462,8 +492,12 @@ __global__ void __launch_bounds__(tcb::kThreads3, 1) ppo_grad_bf16_kernel(const 
       }
       wait_st();
       hand_over(full);
+#if DRONECU_PRIVATE_ISSUER_WARPS
+      gather_rows(row_nxt, cur, 8);
+#else
       if (wq == 0) issue_private<2>(full, done, tmem, 0, dW3p, phf);
       else gather_rows(row_nxt, cur, 8);
+#endif
       TSTAMP(tlog, it, 7);
 
       // ---------------- S3 done: head outputs -> loss gradient at the head ----------------
@@ -515,7 +549,9 @@ __global__ void __launch_bounds__(tcb::kThreads3, 1) ppo_grad_bf16_kernel(const 
       wait_st();
       hand_over(fullA);
       gather_rows(row_nxt, cur, 12);
+#if !DRONECU_PRIVATE_ISSUER_WARPS
       if (wq == 0) gather_rows(row_nxt, cur, 4);
+#endif
       gather_scalars(row_nxt, cur);                        // this tile's act / old_logp / adv / ret live in locals since the top
       TSTAMP(tlog, it, 9);
 
@@ -545,7 +581,9 @@ __global__ void __launch_bounds__(tcb::kThreads3, 1) ppo_grad_bf16_kernel(const 
       }
       wait_st();
       hand_over(fullA);
+#if !DRONECU_PRIVATE_ISSUER_WARPS
       if (wq == 0) gather_rows(row_nxt, cur, 8);
+#endif
       TSTAMP(tlog, it, 11);
 
       // ---------------- S5 done: dZ1 = dH1 * (1 - H1^2) -> bufA (bf16, A of S6) ----------------
