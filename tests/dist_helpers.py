@@ -1,4 +1,4 @@
-"""Host-side helpers of the multi-GPU path (one process per GPU, torch.distributed): how envs are
+"""TEST HELPERS (world_size-2 gloo tests; the product's exchange is csrc/ppo_dp.cuh + drone_rl_b200/ppo.py).  Host-side helpers of the multi-GPU path (one process per GPU, torch.distributed): how envs are
 sharded and how per-rank sums combine.  Pure torch -- they run on CPU under gloo in the tests and
 on GPU under NCCL in bench.py / ppo.py.  Envs shard by contiguous global-id ranges with NO
 collective in the step; the only exchanges are the flat-gradient / advantage-sum

@@ -11,7 +11,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from drone_rl_b200 import dist_utils as du
+from tests import dist_helpers as du
 from oracle import drone_oracle as do
 from oracle import ppo_oracle as po
 
