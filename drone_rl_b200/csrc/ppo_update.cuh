@@ -576,20 +576,34 @@ __global__ void __launch_bounds__(32 * kPartWarps) part_hist_kernel(uint32_t n, 
 }
 
 __global__ void __launch_bounds__(1024) part_scan_kernel(uint32_t* __restrict__ H, uint32_t len) {
-  __shared__ uint32_t part[1024];
-  const uint32_t per = (len + 1023) / 1024, lo = min(len, threadIdx.x * per), hi = min(len, lo + per);
-  uint32_t sum = 0;
-  for (uint32_t i = lo; i < hi; ++i) sum += H[i];
-  part[threadIdx.x] = sum;
+  // one CTA walks H in tiles of 1024 consecutive elements (coalesced), a shuffle scan per warp + a scan of the 32 warp totals
+  // per tile, a running carry across the tiles
+  __shared__ uint32_t wsum[32];
+  __shared__ uint32_t carry_s;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry_s = 0;
   __syncthreads();
-  for (uint32_t off = 1; off < 1024; off <<= 1) {                   // Hillis-Steele inclusive scan of the 1024 segment sums
-    const uint32_t v = threadIdx.x >= off ? part[threadIdx.x - off] : 0;
+  for (uint32_t base = 0; base < len; base += 1024) {
+    const uint32_t i = base + threadIdx.x;
+    const uint32_t v = i < len ? H[i] : 0u;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (uint32_t)o) incl += t; }
+    if (lane == 31) wsum[warp] = incl;
     __syncthreads();
-    part[threadIdx.x] += v;
+    if (warp == 0) {
+      uint32_t w = wsum[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= (uint32_t)o) w += t; }
+      wsum[lane] = w;                                   // inclusive scan of the warp totals
+    }
+    __syncthreads();
+    const uint32_t carry = carry_s;
+    if (i < len) H[i] = carry + (warp ? wsum[warp - 1] : 0u) + incl - v;        // exclusive prefix
+    __syncthreads();
+    if (threadIdx.x == 0) carry_s = carry + wsum[31];
     __syncthreads();
   }
-  uint32_t run = part[threadIdx.x] - sum;                           // exclusive prefix of this thread's segment
-  for (uint32_t i = lo; i < hi; ++i) { const uint32_t v = H[i]; H[i] = run; run += v; }
 }
 
 __global__ void __launch_bounds__(32 * kPartWarps) part_scatter_kernel(uint32_t n, uint32_t batch, uint32_t n_bins, uint32_t rows_per_warp,
