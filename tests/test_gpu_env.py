@@ -558,3 +558,31 @@ def test_render_returns_the_reference_scenes(drl):
     imgb = np.asarray(venv.render()).reshape(-1, 3)
     assert bool((imgb == np.array((0, 160, 0))).all(1).any()) and bool((imgb == np.array((220, 0, 0))).all(1).any())
     venv.close()
+
+
+def test_vecenv_with_observations_kept_on_the_device(drl):
+    """DroneVecEnv(obs_device=True): observations stay on the GPU (a CUDA tensor), rewards / dones arrive as numpy -- the
+    same numbers as the numpy protocol, with numpy or CUDA actions."""
+    n = 3000
+    rng = np.random.default_rng(5)
+    host = drl.DroneVecEnv(n, seed=12, info_mode="arrays")
+    dev = drl.DroneVecEnv(n, seed=12, info_mode="arrays", obs_device=True)
+    dev2 = drl.DroneVecEnv(n, seed=12, info_mode="none", obs_device=True, copy=False)
+    o_h, o_d, o_d2 = host.reset(), dev.reset(), dev2.reset()
+    assert isinstance(o_d, torch.Tensor) and o_d.is_cuda and np.array_equal(o_h, o_d.cpu().numpy()) and torch.equal(o_d, o_d2)
+    n_done = 0
+    for _ in range(40):
+        a = rng.uniform(0, 7.3575, (n, 4)).astype(np.float32)
+        oh, rh, dh, ih = host.step(a)
+        od, rd, dd, idv = dev.step(a)
+        od2, rd2, dd2, i2 = dev2.step(torch.from_numpy(a).cuda())            # actions already on the device: no copy at all
+        assert np.array_equal(oh, od.cpu().numpy()) and np.array_equal(rh, rd) and np.array_equal(dh, dd)
+        assert np.array_equal(ih["truncated"], idv["truncated"]) and i2 == {}
+        assert torch.equal(od, od2) and np.array_equal(rd, rd2) and np.array_equal(dd, dd2)
+        assert rd.dtype == np.float32 and dd.dtype == np.bool_
+        n_done += int(dh.sum())
+    assert n_done > 100
+    with pytest.raises(ValueError):
+        drl.DroneVecEnv(4, obs_device=True)                                  # SB3 info dicts need host terminal observations
+    for e in (host, dev, dev2):
+        e.close()

@@ -392,3 +392,66 @@ def test_minibatch_partition_matches_oracle(drl, n, batch):
             assert (np.diff(seg) > 0).all() and len(seg) == min(batch, n - b * batch)
     assert lib.dronecu_minibatch_partition(h, 6500, 100, 1, 0, C.c_void_p(out.data_ptr()), None) != 0      # 65 minibatches: unsupported
     lib.dronecu_ppo_destroy(h)
+
+
+def test_learn_counts_timesteps_like_sb3(drl):
+    """SB3's learn(total_timesteps) trains that many MORE steps: reset_num_timesteps=True (default) restarts the counter, so
+    PPO.load(...).learn(T) after a resume (reference train.py:22-30, :63-68) does not return at once; False continues it."""
+    from drone_rl_b200.ppo import PPO
+    model = PPO(drl.DroneBatch(64, drl.EnvConfig.single(), seed=2), n_steps=16, batch_size=256, n_epochs=2, seed=2)
+    per_iter = 64 * 16
+    model.learn(3 * per_iter)
+    assert model.num_timesteps == 3 * per_iter and model.n_updates == 3 * 2 * 4
+    model.learn(2 * per_iter)                                   # counter restarts; two more iterations
+    assert model.num_timesteps == 2 * per_iter and model.n_updates == 5 * 2 * 4
+    model.learn(per_iter, reset_num_timesteps=False)            # continues: one more iteration on top
+    assert model.num_timesteps == 3 * per_iter and model.n_updates == 6 * 2 * 4
+    assert model.logger_values["time/total_timesteps"] == 3 * per_iter
+    model.close()
+
+
+def test_checkpoint_env_state_only_onto_the_same_shard(drl, tmp_path):
+    """The env / curriculum / Philox state of an archive belongs to ONE shard of global env ids (its env_offset and world size
+    travel with it): a handle over other env ids starts fresh instead of becoming a copy of shard 0; policy and Adam load
+    either way."""
+    from drone_rl_b200.ppo import PPO
+    n = 128
+    a = PPO(drl.DroneBatch(n, drl.EnvConfig.single(), seed=4, env_offset=0), n_steps=8, batch_size=256, n_epochs=1, seed=4)
+    a.learn(4 * n * 8)
+    path = str(tmp_path / "shard0.zip")
+    a.save(path)
+    same = PPO.load(path, drl.DroneBatch(n, drl.EnvConfig.single(), seed=4, env_offset=0), n_steps=8, batch_size=256, n_epochs=1)
+    other = PPO.load(path, drl.DroneBatch(n, drl.EnvConfig.single(), seed=4, env_offset=n), n_steps=8, batch_size=256, n_epochs=1)
+    assert same.env_state_restored and not other.env_state_restored
+    assert torch.equal(same.params, a.params) and torch.equal(other.params, a.params)
+    assert np.array_equal(same.batch.get_state("ep_num")["ep_num"], a.batch.get_state("ep_num")["ep_num"])
+    assert (other.batch.get_state("ep_num")["ep_num"] == 2).all()          # fresh: constructor reset + PPO's reset
+    for m in (a, same, other):
+        m.close()
+
+
+def test_train_logs_the_mean_over_all_minibatches(drl):
+    """SB3 logs np.mean over every minibatch of every epoch for policy_gradient_loss / value_loss / approx_kl / clip_fraction
+    and the LAST minibatch's total loss; the device-side accumulator must give exactly that."""
+    from drone_rl_b200.ppo import PPO
+    model = PPO(drl.DroneBatch(512, drl.EnvConfig.single(), seed=6), n_steps=16, batch_size=1024, n_epochs=3, seed=6, cuda_graph=False)
+    model.collect_rollouts()
+    seen, orig = [], model._minibatch
+
+    def spy(index, first, m, stats=None):
+        orig(index, first, m, stats)
+        seen.append(model._info.cpu().numpy().copy())
+    model._minibatch = spy
+    model.train()
+    seen = np.array(seen)
+    assert seen.shape[0] == 3 * 8
+    lv = model.logger_values
+    for k, col in (("train/policy_gradient_loss", 0), ("train/value_loss", 1), ("train/approx_kl", 2), ("train/clip_fraction", 3), ("train/grad_norm", 8)):
+        np.testing.assert_allclose(lv[k], seen[:, col].mean(), rtol=2e-6, atol=1e-9, err_msg=k)
+    ent = -float((0.5 + 0.5 * np.log(2 * np.pi) + model.params[-4:].cpu().numpy().astype(np.float64)).sum())
+    np.testing.assert_allclose(lv["train/entropy_loss"], ent, rtol=1e-6)
+    np.testing.assert_allclose(lv["train/loss"], seen[-1, 0] + 0.5 * seen[-1, 1] + 0.0 * ent, rtol=1e-6, atol=1e-9)
+    b = model.buf
+    y, v = b.ret.cpu().double().numpy().ravel(), b.value.cpu().double().numpy().ravel()
+    np.testing.assert_allclose(lv["train/explained_variance"], 1 - np.var(y - v) / np.var(y), rtol=1e-4, atol=1e-5)
+    model.close()
