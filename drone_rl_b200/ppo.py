@@ -23,6 +23,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import sys
 import time
 from typing import Optional
 
@@ -189,16 +190,33 @@ class PPO:
             return
         if self.world > _lib.DP_MAX_WORLD:
             raise ValueError(f"dp_backend='peer' supports at most {_lib.DP_MAX_WORLD} ranks (one NVLink domain)")
-        handle = (C.c_ubyte * _lib.IPC_HANDLE_BYTES)()
-        _lib.check(self.lib.dronecu_ppo_dp_alloc(self._h, self.rank, self.world, handle, None), "dronecu_ppo_dp_alloc")
-        h = torch.tensor(list(bytes(handle)), dtype=torch.uint8, device=self.device)
+        # peers must be reachable through CUDA IPC + peer access (the GPUs of one NVLink box); if any rank cannot map its
+        # peers (another node, IPC disabled in a container) EVERY rank falls back to the NCCL backend, together
+        ok, why = 1, ""
+        try:
+            handle = (C.c_ubyte * _lib.IPC_HANDLE_BYTES)()
+            _lib.check(self.lib.dronecu_ppo_dp_alloc(self._h, self.rank, self.world, handle, None), "dronecu_ppo_dp_alloc")
+            h = torch.tensor(list(bytes(handle)), dtype=torch.uint8, device=self.device)
+        except _lib.DronecuError as e:
+            ok, why, h = 0, str(e), torch.zeros(_lib.IPC_HANDLE_BYTES, dtype=torch.uint8, device=self.device)
         allh = [torch.zeros_like(h) for _ in range(self.world)]
         dist.all_gather(allh, h)
-        blob = b"".join(bytes(t.cpu().tolist()) for t in allh)
-        buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
-        _lib.check(self.lib.dronecu_ppo_dp_connect(self._h, self.world, buf, None), "dronecu_ppo_dp_connect")
+        if ok:
+            try:
+                blob = b"".join(bytes(t.cpu().tolist()) for t in allh)
+                buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+                _lib.check(self.lib.dronecu_ppo_dp_connect(self._h, self.world, buf, None), "dronecu_ppo_dp_connect")
+            except _lib.DronecuError as e:
+                ok, why = 0, str(e)
+        flag = torch.tensor([ok], dtype=torch.int32, device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         torch.cuda.synchronize(self.device)
         dist.barrier()                             # every mailbox is zeroed and mapped before the first push
+        if int(flag.item()) == 0:
+            if self.rank == 0 or why:
+                print(f"[drone_rl_b200] rank {self.rank}: peer-memory exchange unavailable ({why or 'another rank failed'}); "
+                      "using dp_backend='nccl'", file=sys.stderr, flush=True)
+            self.dp_backend = "nccl"
 
     def _allreduce_f64(self, t: torch.Tensor):
         """In-place sum over the ranks of a small float64 device tensor (advantage / episode statistics)."""
