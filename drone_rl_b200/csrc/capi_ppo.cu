@@ -30,7 +30,7 @@ struct dronecu_ppo {
   double* adv_partials; // [n_sm * 8, 2]
   uint32_t* part_hist;  // scratch of dronecu_minibatch_partition (grown on demand)
   size_t part_hist_len;
-  long long* d_step; // device-resident Adam step count (ppo_apply_kernel increments it)
+  long long* d_step; // device-resident AdamClock {step count, beta1^step, beta2^step} (ppo_apply*_kernel advance it)
   uint64_t launches;
   float* dbg;        // see dronecu_ppo_debug_buffer
   float* info_sum;   // see dronecu_ppo_set_info_accumulator (caller-owned, nullable)
@@ -154,8 +154,11 @@ extern "C" int dronecu_ppo_create(const dronecu_ppo_config* cfg, int device, dro
   CUDA_TRY(cudaMalloc(&p->moments, sizeof(float) * 2 * kParams));
   CUDA_TRY(cudaMalloc(&p->adv_partials, sizeof(double) * 2 * (size_t)p->n_sm * 8));
   CUDA_TRY(cudaMemset(p->moments, 0, sizeof(float) * 2 * kParams));
-  CUDA_TRY(cudaMalloc(&p->d_step, sizeof(long long)));
-  CUDA_TRY(cudaMemset(p->d_step, 0, sizeof(long long)));
+  CUDA_TRY(cudaMalloc(&p->d_step, sizeof(AdamClock)));
+  {
+    const AdamClock c0 = {0, 1.0, 1.0};
+    CUDA_TRY(cudaMemcpy(p->d_step, &c0, sizeof(c0), cudaMemcpyHostToDevice));
+  }
   CUDA_TRY(cudaFuncSetAttribute(ppo_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UpdSmem)));
   CUDA_TRY(cudaFuncSetAttribute(ppo_grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcUpdSmem));
   CUDA_TRY(cudaFuncSetAttribute(ppo_grad_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTc3Smem));
@@ -385,7 +388,7 @@ extern "C" int dronecu_ppo_set_state(dronecu_ppo* p, const float* d_moments, int
   DeviceGuard guard(p->device);
   if (d_moments)
     CUDA_TRY(cudaMemcpyAsync(p->moments, d_moments, sizeof(float) * 2 * kParams, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
-  const long long t = step;
+  const AdamClock t = {(long long)step, std::pow((double)p->cfg.beta1, (double)step), std::pow((double)p->cfg.beta2, (double)step)};
   CUDA_TRY(cudaMemcpyAsync(p->d_step, &t, sizeof(t), cudaMemcpyHostToDevice, (cudaStream_t)stream));
   CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
   return DRONECU_OK;

@@ -127,11 +127,11 @@ __global__ void __launch_bounds__(kDpBlock) ppo_apply_dp_kernel(const __grid_con
     grad_io[i] = acc;
   }
   if (threadIdx.x == 0) {
-    const long long t = *A.step + 1;
-    *A.step = t;
-    const double bc1 = 1.0 - pow((double)A.beta1, (double)t), bc2 = 1.0 - pow((double)A.beta2, (double)t);
-    lr_over_bc1_s = (float)((double)A.lr / bc1);
-    inv_sqrt_bc2_s = (float)(1.0 / sqrt(bc2));
+    AdamClock* clk = reinterpret_cast<AdamClock*>(A.step);
+    const double p1 = clk->b1pow * (double)A.beta1, p2 = clk->b2pow * (double)A.beta2;
+    clk->step += 1; clk->b1pow = p1; clk->b2pow = p2;
+    lr_over_bc1_s = (float)((double)A.lr / (1.0 - p1));
+    inv_sqrt_bc2_s = (float)(1.0 / sqrt(1.0 - p2));
   }
   __syncthreads();
   const float inv_count = 1.0f / g_s[kParams + 4];
@@ -146,22 +146,12 @@ __global__ void __launch_bounds__(kDpBlock) ppo_apply_dp_kernel(const __grid_con
   if (threadIdx.x < 32) {
     float v = red[threadIdx.x];
     v = warp_sum(v);
-    if (threadIdx.x == 0) {
-      const float norm = sqrtf(v);
-      coef_s = fminf(A.max_norm / (norm + 1e-6f), 1.0f);
-      if (A.info) {
-        for (int q = 0; q < kStats; ++q) A.info[q] = g_s[kParams + q] * (q == 4 ? 1.0f : inv_count);
-        A.info[kStats] = norm;
-      }
-      if (A.info_sum) {
-        for (int q = 0; q < kStats; ++q) A.info_sum[q] += g_s[kParams + q] * (q == 4 ? 1.0f : inv_count);
-        A.info_sum[kStats] += norm;
-        A.info_sum[kStats + 1] += 1.0f;
-      }
-    }
+    if (threadIdx.x == 0) coef_s = sqrtf(v);          // the pre-clip gradient norm
   }
   __syncthreads();
-  const float coef = coef_s * inv_count;
+  const float norm = coef_s;
+  apply_publish_info(A, g_s + kParams, inv_count, norm);
+  const float coef = fminf(A.max_norm / (norm + 1e-6f), 1.0f) * inv_count;
   const float lr_over_bc1 = lr_over_bc1_s, inv_sqrt_bc2 = inv_sqrt_bc2_s;
   for (int i = threadIdx.x; i < kParams; i += kDpBlock) {
     const float g = g_s[i] * coef;

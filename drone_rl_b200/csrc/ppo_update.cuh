@@ -453,22 +453,44 @@ struct AdamArgs {
   float* theta; const float* grad; float* m; float* v;
   float inv_count;           // 1 / (global number of samples in the minibatch)
   float lr, beta1, beta2, eps, max_norm;
-  long long* step;           // device-resident Adam step count (incremented here: the launch sequence is CUDA-graph capturable)
+  long long* step;           // device-resident AdamClock {step, beta1^step, beta2^step} (advanced here: the launch sequence is CUDA-graph capturable)
   float* info;               // [kStats + 1]: mean statistics + pre-clip gradient norm of THIS step (nullable)
   float* info_sum;           // [kStats + 2]: the same values ACCUMULATED over the steps + the number of steps (nullable):
                              // SB3 logs the mean over all minibatches of PPO.train(), not the last one
 };
 
+// Adam's bias corrections 1 - beta^t: the powers are kept as running float64 products next to the step count
+// ([step][beta1^t][beta2^t], 24 bytes; dronecu_ppo_set_state recomputes them with pow on the host) -- a device-side double
+// pow per optimiser step sat on the critical path of this single-CTA kernel.
+struct AdamClock { long long step; double b1pow, b2pow; };
+
+// statistics of one optimiser step: threads 0 .. kStats+1 each handle ONE entry (one thread walking ten dependent global
+// read-modify-writes was half of this kernel's 19 us)
+__device__ __forceinline__ void apply_publish_info(const AdamArgs& A, const float* stats /* [kStats] sums */, const float inv_count,
+                                                   const float norm) {
+  const int q = threadIdx.x;
+  if (q < kStats) {
+    const float v = stats[q] * (q == 4 ? 1.0f : inv_count);
+    if (A.info) A.info[q] = v;
+    if (A.info_sum) A.info_sum[q] += v;
+  } else if (q == kStats) {
+    if (A.info) A.info[kStats] = norm;
+    if (A.info_sum) A.info_sum[kStats] += norm;
+  } else if (q == kStats + 1) {
+    if (A.info_sum) A.info_sum[kStats + 1] += 1.0f;
+  }
+}
+
 // torch.nn.utils.clip_grad_norm_(max_norm) + torch.optim.Adam.step() on the flat vector (one CTA)
 __global__ void __launch_bounds__(1024) ppo_apply_kernel(const AdamArgs A) {
   __shared__ float red[32];
-  __shared__ float coef_s, lr_over_bc1_s, inv_sqrt_bc2_s;
-  if (threadIdx.x == 0) {      // torch.optim.Adam bias corrections of step t = ++(*step)
-    const long long t = *A.step + 1;
-    *A.step = t;
-    const double bc1 = 1.0 - pow((double)A.beta1, (double)t), bc2 = 1.0 - pow((double)A.beta2, (double)t);
-    lr_over_bc1_s = (float)((double)A.lr / bc1);
-    inv_sqrt_bc2_s = (float)(1.0 / sqrt(bc2));
+  __shared__ float norm_s, lr_over_bc1_s, inv_sqrt_bc2_s;
+  if (threadIdx.x == 0) {      // torch.optim.Adam bias corrections of step t = ++step
+    AdamClock* clk = reinterpret_cast<AdamClock*>(A.step);
+    const double p1 = clk->b1pow * (double)A.beta1, p2 = clk->b2pow * (double)A.beta2;
+    clk->step += 1; clk->b1pow = p1; clk->b2pow = p2;
+    lr_over_bc1_s = (float)((double)A.lr / (1.0 - p1));
+    inv_sqrt_bc2_s = (float)(1.0 / sqrt(1.0 - p2));
   }
   float sq = 0.f;
   for (int i = threadIdx.x; i < kParams; i += blockDim.x) {
@@ -481,22 +503,12 @@ __global__ void __launch_bounds__(1024) ppo_apply_kernel(const AdamArgs A) {
   if (threadIdx.x < 32) {
     float v = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
     v = warp_sum(v);
-    if (threadIdx.x == 0) {
-      const float norm = sqrtf(v);
-      coef_s = fminf(A.max_norm / (norm + 1e-6f), 1.0f);
-      if (A.info) {
-        for (int q = 0; q < kStats; ++q) A.info[q] = A.grad[kParams + q] * (q == 4 ? 1.0f : A.inv_count);
-        A.info[kStats] = norm;
-      }
-      if (A.info_sum) {
-        for (int q = 0; q < kStats; ++q) A.info_sum[q] += A.grad[kParams + q] * (q == 4 ? 1.0f : A.inv_count);
-        A.info_sum[kStats] += norm;
-        A.info_sum[kStats + 1] += 1.0f;
-      }
-    }
+    if (threadIdx.x == 0) norm_s = sqrtf(v);
   }
   __syncthreads();
-  const float coef = coef_s * A.inv_count;
+  const float norm = norm_s;
+  apply_publish_info(A, A.grad + kParams, A.inv_count, norm);
+  const float coef = fminf(A.max_norm / (norm + 1e-6f), 1.0f) * A.inv_count;
   const float lr_over_bc1 = lr_over_bc1_s, inv_sqrt_bc2 = inv_sqrt_bc2_s;
   for (int i = threadIdx.x; i < kParams; i += blockDim.x) {
     const float g = A.grad[i] * coef;
