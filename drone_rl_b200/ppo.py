@@ -412,7 +412,8 @@ class PPO:
             it += 1
             self.logger_values.update({"rollout/ep_rew_mean": st["ep_rew_mean"], "rollout/ep_len_mean": st["ep_len_mean"],
                                        "time/iterations": it, "time/total_timesteps": self.num_timesteps,
-                                       "time/fps": int((self.num_timesteps - start) / max(time.time() - t0, 1e-9))})
+                                       "time/fps": int((self.num_timesteps - start) / max(time.time() - t0, 1e-9)),
+                                       "time/time_elapsed": int(time.time() - t0)})
             if callback is not None and callback(self) is False:
                 break
             if self.verbose and self.rank == 0 and it % log_interval == 0:
