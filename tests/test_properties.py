@@ -1,0 +1,136 @@
+"""Property tests (hypothesis): the semantics that single examples miss.
+
+CPU half (``-m "not gpu"``): the float64 oracle against the LIVE unmodified reference (where it is present: the build
+container's /root/reference or the staged oracle/_ref archive) on generated states -- finite, huge, sub-normal, inf, NaN:
+bit-identical next state / reward / done for the vectorized env, NaN never terminates (drone.py:154), the time limit takes
+precedence (drone.py:156-157), 0 * inf = NaN in the body-rate / Euler-rate terms (drone.py:138, :181-186).
+GPU half: one teacher-forced CUDA step from generated float32 states against the oracle: identical NaN / inf pattern,
+identical done bits away from the thresholds, values within 1e-5 * max(|ref|, 1, term magnitudes).
+"""
+import numpy as np
+import pytest
+from hypothesis import HealthCheck, given, settings
+from hypothesis import strategies as st
+from hypothesis.extra import numpy as hnp
+
+from oracle import drone_oracle as do
+from oracle import ref_import, verify
+
+np.seterr(all="ignore")
+
+finite32 = st.floats(min_value=-1e6, max_value=1e6, allow_nan=False, allow_infinity=False, width=32)
+wild32 = st.one_of(finite32, st.floats(width=32, allow_nan=True, allow_infinity=True),
+                   st.sampled_from([0.0, -0.0, np.float32(np.pi / 2), np.float32(-np.pi / 2), 1e-40, 3e38, 50.0, -1e-7]))
+
+
+def _states(n, elements):
+    return st.tuples(*(hnp.arrays(np.float32, (n, 3), elements=elements) for _ in range(4)),
+                     hnp.arrays(np.float32, (n, 4), elements=st.floats(min_value=-2.0, max_value=9.0, width=32)))
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="the reference is not present (neither /root/reference nor oracle/_ref)")
+@settings(max_examples=60, deadline=None, suppress_health_check=list(HealthCheck))
+@given(_states(8, wild32))
+def test_oracle_equals_live_reference_on_wild_states(s):
+    pos, vel, eul, om, act = s
+    _, vd = ref_import.load()
+    ref, orc = vd.VectorizedDroneEnv(8), do.BatchedDroneOracle(8, do.VECTOR)
+    ref.reset(); orc.reset()
+    ref.pos, ref.vel, ref.euler, ref.omega = (a.astype(np.float64).copy() for a in (pos, vel, eul, om))
+    orc.set_state(pos, vel, eul, om, None, step_count=0)
+    o1, r1, d1, _ = ref.step(act.astype(np.float64))
+    o2, r2, d2, _ = orc.step(act)
+    assert np.array_equal(o1, o2, equal_nan=True) and np.array_equal(r1, r2, equal_nan=True) and np.array_equal(d1, d2)
+    z, rad = ref.pos[:, 2], np.linalg.norm(ref.pos, axis=1)
+    assert np.array_equal(d1, (z < 0) | (rad > 50)), "done == (z < 0) | (|pos| > 50): NaN compares false (vectorized_drone.py:211)"
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="the reference is not present")
+@settings(max_examples=40, deadline=None, suppress_health_check=list(HealthCheck))
+@given(hnp.arrays(np.float32, (3,), elements=wild32), hnp.arrays(np.float32, (3,), elements=wild32),
+       st.integers(min_value=0, max_value=199))
+def test_single_env_time_limit_takes_precedence_and_nan_never_crashes(pos, om, step):
+    drone, _ = ref_import.load()
+    env = drone.DroneEnv()
+    env.pos, env.omega = pos.astype(np.float64), om.astype(np.float64)
+    env.current_step = step
+    _, rew, done, _ = env.step(np.full(4, 2.4525))
+    crashed = bool(env.pos[2] < 0 or np.linalg.norm(env.pos) > 50)            # NaN compares false: never "crashed"
+    assert done == (crashed or step + 1 >= 200)
+    # the oracle's DroneGymEnv spec (no auto-reset) from the same state: same observation / reward / done
+    spec = do.Spec(do.SINGLE.name, do.SINGLE.obs_dim, do.SINGLE.max_steps, do.SINGLE.bonus_radius, do.SINGLE.curriculum,
+                   do.SINGLE.random_start, do.SINGLE.shared_step, False)
+    orc = do.BatchedDroneOracle(1, spec)
+    env2 = drone.DroneEnv()
+    env2.pos, env2.omega, env2.current_step = pos.astype(np.float64), om.astype(np.float64), step
+    orc.set_state(pos[None], env2.vel[None].astype(np.float32), env2.euler[None].astype(np.float32), om[None],
+                  env2.target[None].astype(np.float32), step_count=np.array([step]))
+    env2.target = env2.target.astype(np.float32).astype(np.float64)            # the oracle holds what set_state was given
+    obs_r, rew_r, done_r, _ = env2.step(np.full(4, 2.4525, np.float32).astype(np.float64))   # the oracle's dtype convention: f32 action, upcast
+    obs_o, rew_o, done_o, _ = orc.step(np.full((1, 4), 2.4525, np.float32))
+    assert bool(done_o[0]) == bool(done_r)
+    assert np.array_equal(np.isnan(obs_o[0]), np.isnan(obs_r))
+    fin = np.isfinite(obs_r)
+    np.testing.assert_allclose(obs_o[0][fin], obs_r[fin], rtol=2e-6, atol=1e-30)
+    if np.isfinite(rew_r):
+        np.testing.assert_allclose(rew_o[0], rew_r, rtol=1e-12, atol=1e-300)
+    else:
+        assert np.isnan(rew_o[0]) == np.isnan(rew_r)
+
+
+@pytest.mark.gpu
+@settings(max_examples=60, deadline=None, suppress_health_check=list(HealthCheck))
+@given(_states(64, wild32), st.sampled_from(["single", "vector"]))
+def test_gpu_step_matches_oracle_on_wild_states(s, which):
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import drone_rl_b200 as drl
+    pos, vel, eul, om, act = s
+    n = 64
+    spec = do.SINGLE if which == "single" else do.VECTOR
+    cfg = drl.EnvConfig.single(auto_reset=False) if which == "single" else drl.EnvConfig.vector()
+    b = drl.DroneBatch(n, cfg, seed=0)
+    tgt = np.tile(np.float32([0.25, -0.5, 1.5]), (n, 1))
+    kw = dict(pos=pos, vel=vel, euler=eul, omega=om, step=np.zeros(n, np.int32), ep_len=np.zeros(n, np.int32), ep_ret=np.zeros(n, np.float32))
+    if which == "single":
+        kw["target"] = tgt
+    b.set_state(**kw)
+    out = b.step(torch.from_numpy(act).cuda())
+    got = {k: v.cpu().numpy() for k, v in out.items()}
+    b.close()
+    p64, v64, e64, o64 = (a.astype(np.float64) for a in (pos, vel, eul, om))
+    npos, nvel, neul, nom = do.dynamics_step(p64, v64, e64, o64, act.astype(np.float64))
+    target = tgt.astype(np.float64) if which == "single" else np.tile(np.array([0.0, 0.0, 10.0]), (n, 1))
+    rew, crashed = do.reward_and_crash(npos, target, spec.bonus_radius)
+    ref = do.build_obs(npos, nvel, neul, nom, target, spec.obs_dim).astype(np.float64)
+    g = got["obs"].astype(np.float64)
+    # float32 overflow: the oracle's float64 value may be finite where |value| exceeds the float32 range -> compare after the cast
+    ref32 = ref.astype(np.float32).astype(np.float64)
+    assert np.array_equal(np.isnan(g), np.isnan(ref32)), "NaN pattern"
+    # values: the checker's tolerance (term magnitudes), on entries that are finite on both sides and not at the float32 edge
+    sphi, cphi, cosp, tanp = np.sin(e64[:, 0]), np.cos(e64[:, 0]), np.cos(e64[:, 1]), np.tan(e64[:, 1])
+    mix = np.abs(o64[:, 1] * sphi) + np.abs(o64[:, 2] * cphi)
+    T = np.zeros_like(ref)
+    T[:, 0:3] = np.abs(p64) + do.DT * (np.abs(v64) + do.DT * 30.0 * 9.0 * 4)           # |p| + dt |v'|
+    T[:, 3:6] = np.abs(v64) + do.DT * (9.81 + 36.0)
+    T[:, 6] = np.abs(e64[:, 0]) + do.DT * (np.abs(o64[:, 0]) + np.abs(tanp) * mix)
+    T[:, 7] = np.abs(e64[:, 1]) + do.DT * mix
+    T[:, 8] = np.abs(e64[:, 2]) + do.DT * np.abs(1.0 / cosp) * mix
+    T[:, 9] = np.abs(o64[:, 0]) + do.DT * (np.abs(o64[:, 1] * o64[:, 2]) + 4000.0)
+    T[:, 10] = np.abs(o64[:, 1]) + do.DT * (np.abs(o64[:, 0] * o64[:, 2]) + 4000.0)
+    T[:, 11] = np.abs(o64[:, 2]) + do.DT * 40.0
+    if spec.obs_dim == 15:
+        T[:, 12:15] = T[:, 0:3] + np.abs(target)
+    ok = np.isfinite(ref32) & np.isfinite(g) & (np.abs(ref) < 1e37) & np.isfinite(T)
+    # huge angles: sin / cos of a float32 angle are exact on both sides, but near-singular pitch amplifies; keep |cos| > 1e-3 rows
+    ok &= (np.abs(cosp) > 1e-3)[:, None] | (np.arange(ref.shape[1])[None, :] < 6)
+    err = np.abs(g - ref)[ok]
+    bound = (1e-5 * np.maximum(np.maximum(np.abs(ref), 1.0), T))[ok]
+    assert (err <= bound).all(), f"worst err/bound {np.max(err / bound):.3g}"
+    # done: identical wherever the decision is not within float32 rounding of a threshold; NaN positions never terminate
+    rad = np.linalg.norm(npos, axis=1)
+    safe = ((np.abs(npos[:, 2]) > 1e-5 * np.maximum(1.0, T[:, 2])) & (np.abs(rad - 50.0) > 1e-4 * np.maximum(1.0, rad * 1e-2))) | ~np.isfinite(rad)
+    safe &= np.isfinite(npos).all(axis=1) | np.isnan(npos).any(axis=1)
+    d_ref = crashed | (1 >= spec.max_steps)
+    assert np.array_equal(got["done"].astype(bool)[safe], d_ref[safe])
