@@ -590,9 +590,12 @@ def ppo_variant(ctx, args, wl, n, K, minibatches, epochs, rollout_precision, upd
     torch, drl, dev, world = ctx.torch, ctx.drl, ctx.dev, ctx.world
     from drone_rl_b200.ppo import PPO
     env = drl.DroneBatch(n, drl.EnvConfig.single(), device=ctx.local, seed=args.seed, env_offset=ctx.rank * n)
-    model = PPO(env, n_steps=K, batch_size=n * K // minibatches, n_epochs=epochs, seed=args.seed,
-                rollout_precision=rollout_precision, update_precision=update_precision, dp_backend=args.dp_backend)
     full = wl in ("c5", "c1")
+    # c3 collects rollouts only: no update kernel follows, so the buffer keeps SB3's packed 60-byte observation rows (the 64-byte
+    # rows are the bf16 update kernel's input format: c5 / c1 take the model's default)
+    model = PPO(env, n_steps=K, batch_size=n * K // minibatches, n_epochs=epochs, seed=args.seed,
+                rollout_precision=rollout_precision, update_precision=update_precision, dp_backend=args.dp_backend,
+                padded_obs=None if full else False)
 
     debug = os.environ.get("DRONECU_BENCH_DEBUG") == "1"
 

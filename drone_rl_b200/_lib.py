@@ -57,7 +57,7 @@ class StateView(C.Structure):
 class PolicyOut(C.Structure):
     _fields_ = [("d_obs", C.c_void_p), ("d_actions", C.c_void_p), ("d_logp", C.c_void_p), ("d_value", C.c_void_p),
                 ("d_reward", C.c_void_p), ("d_done", C.c_void_p), ("d_last_value", C.c_void_p),
-                ("d_last_obs", C.c_void_p)]
+                ("d_last_obs", C.c_void_p), ("obs_padded", C.c_int32), ("reserved", C.c_int32)]
 
 
 class PPOConfig(C.Structure):
@@ -118,6 +118,7 @@ _SIGNATURES = {
     "dronecu_ppo_grad": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int64, C.c_float, C.c_float, _P, _P, _P]),
     "dronecu_ppo_grad_tc": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int64, C.c_float, C.c_float, _P, _P, _P]),
     "dronecu_ppo_grad_bf16": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int64, C.c_float, C.c_float, _P, _P, _P]),
+    "dronecu_ppo_grad_strided": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int64, C.c_float, C.c_float, _P, _P, _P]),
     "dronecu_ppo_debug_buffer": (C.c_int, [_P, _P]),
     "dronecu_ppo_apply": (C.c_int, [_P, _P, _P, C.c_double, _P, _P]),
     "dronecu_ppo_num_updates": (C.c_int64, [_P]),

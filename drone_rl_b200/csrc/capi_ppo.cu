@@ -48,13 +48,16 @@ static int rollout_policy_impl(dronecu_env* e, int K, const float* d_params, int
     return fail(DRONECU_ERR_UNSUPPORTED, "policy rollout needs the 15-dim observation and DRONECU_AUTORESET");
   if (out && out->d_actions && (reinterpret_cast<uintptr_t>(out->d_actions) & 15))
     return fail(DRONECU_ERR_INVALID, "out->d_actions must be 16-byte aligned");
+  if (out && out->obs_padded && out->d_obs && (reinterpret_cast<uintptr_t>(out->d_obs) & 15))
+    return fail(DRONECU_ERR_INVALID, "padded out->d_obs must be 16-byte aligned");
   DeviceGuard guard(e->device);
   PolicyArgs a;
   std::memset(&a, 0, sizeof(a));
   a.state = e->sp; a.P = e->P; a.n = e->n; a.K = K; a.t0 = e->t; a.theta = d_params; a.deterministic = deterministic;
   a.stats = e->stats;
   if (out) {
-    a.obs = out->d_obs; a.actions = reinterpret_cast<float4*>(out->d_actions); a.logp = out->d_logp;
+    a.obs = out->d_obs; a.obs_padded = out->obs_padded ? 1 : 0;
+    a.actions = reinterpret_cast<float4*>(out->d_actions); a.logp = out->d_logp;
     a.value = out->d_value; a.reward = out->d_reward; a.done = out->d_done; a.last_value = out->d_last_value;
     a.last_obs = out->d_last_obs;
   }
@@ -161,7 +164,8 @@ extern "C" int dronecu_ppo_create(const dronecu_ppo_config* cfg, int device, dro
   }
   CUDA_TRY(cudaFuncSetAttribute(ppo_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UpdSmem)));
   CUDA_TRY(cudaFuncSetAttribute(ppo_grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcUpdSmem));
-  CUDA_TRY(cudaFuncSetAttribute(ppo_grad_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTc3Smem));
+  CUDA_TRY(cudaFuncSetAttribute(ppo_grad_bf16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTc3Smem));
+  CUDA_TRY(cudaFuncSetAttribute(ppo_grad_bf16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTc3Smem));
   *out = p;
   return DRONECU_OK;
 }
@@ -284,15 +288,17 @@ extern "C" int dronecu_ppo_adv_stats_epoch(dronecu_ppo* p, const float* d_adv, c
 static int ppo_grad_impl(dronecu_ppo* p, const float* d_params, const float* d_obs, const float* d_actions,
                          const float* d_old_logp, const float* d_adv, const float* d_returns,
                          const int32_t* d_index, int64_t first, int64_t m, float adv_mean, float adv_inv_std,
-                         const double* d_adv_stats, float* d_grad, void* stream, int mode) {
+                         const double* d_adv_stats, float* d_grad, void* stream, int mode, int obs_stride = 15) {
   const bool tensor_cores = mode != 0;
+  if (obs_stride != 15 && obs_stride != 16) return fail(DRONECU_ERR_INVALID, "dronecu_ppo_grad: obs_stride must be 15 (packed rows) or 16 (64-byte rows)");
+  if (obs_stride == 16 && (reinterpret_cast<uintptr_t>(d_obs) & 15)) return fail(DRONECU_ERR_INVALID, "padded d_obs must be 16-byte aligned");
   if (!p || !d_params || !d_obs || !d_actions || !d_old_logp || !d_adv || !d_returns || !d_grad || m <= 0)
     return fail(DRONECU_ERR_INVALID, "dronecu_ppo_grad: bad argument");
   if (reinterpret_cast<uintptr_t>(d_actions) & 15) return fail(DRONECU_ERR_INVALID, "d_actions must be 16-byte aligned");
   if (first < 0 || first + m > ((int64_t)1 << 31) - 1) return fail(DRONECU_ERR_INVALID, "dronecu_ppo_grad: row numbers must fit in 31 bits");
   DeviceGuard guard(p->device);
   UpdArgs a;
-  a.theta = d_params; a.obs = d_obs; a.actions = reinterpret_cast<const float4*>(d_actions); a.old_logp = d_old_logp;
+  a.theta = d_params; a.obs = d_obs; a.obs_stride = obs_stride; a.actions = reinterpret_cast<const float4*>(d_actions); a.old_logp = d_old_logp;
   a.adv = d_adv; a.ret = d_returns; a.index = d_index; a.first = first; a.m = m;
   a.adv_mean = adv_mean; a.adv_inv_std = adv_inv_std; a.adv_stats = d_adv_stats;
   a.clip = p->cfg.clip_range; a.vf_coef = p->cfg.vf_coef; a.ent_coef = p->cfg.ent_coef;
@@ -302,7 +308,8 @@ static int ppo_grad_impl(dronecu_ppo* p, const float* d_params, const float* d_o
   if (mode == 2) {
     // grid (x, 2): blockIdx.y = tower; one CTA per SM, three 128-sample tiles in flight per CTA, one partial vector per CTA
     const unsigned gx = (unsigned)std::max<int64_t>(1, std::min<int64_t>((tiles + tcb::kWG3 - 1) / tcb::kWG3, p->n_sm / 2));
-    ppo_grad_bf16_kernel<<<dim3(gx, 2), tcb::kThreads3, kTc3Smem, st>>>(a);
+    if (obs_stride == 16) ppo_grad_bf16_kernel<true><<<dim3(gx, 2), tcb::kThreads3, kTc3Smem, st>>>(a);
+    else ppo_grad_bf16_kernel<false><<<dim3(gx, 2), tcb::kThreads3, kTc3Smem, st>>>(a);
     CUDA_TRY(cudaGetLastError());
     ppo_reduce_tc_kernel<<<(kGradLen + 255) / 256, 256, 0, st>>>(p->partials, (int)gx, d_grad);
   } else if (tensor_cores) {
@@ -344,6 +351,15 @@ extern "C" int dronecu_ppo_grad_bf16(dronecu_ppo* p, const float* d_params, cons
                                      const double* d_adv_stats, float* d_grad, void* stream) {
   return ppo_grad_impl(p, d_params, d_obs, d_actions, d_old_logp, d_adv, d_returns, d_index, first, m, adv_mean,
                        adv_inv_std, d_adv_stats, d_grad, stream, 2);
+}
+
+extern "C" int dronecu_ppo_grad_strided(dronecu_ppo* p, int mode, int obs_stride, const float* d_params, const float* d_obs,
+                                        const float* d_actions, const float* d_old_logp, const float* d_adv, const float* d_returns,
+                                        const int32_t* d_index, int64_t first, int64_t m, float adv_mean, float adv_inv_std,
+                                        const double* d_adv_stats, float* d_grad, void* stream) {
+  if (mode < 0 || mode > 2) return fail(DRONECU_ERR_INVALID, "dronecu_ppo_grad_strided: mode must be 0 (fp32), 1 (tf32) or 2 (bf16 wgrad)");
+  return ppo_grad_impl(p, d_params, d_obs, d_actions, d_old_logp, d_adv, d_returns, d_index, first, m, adv_mean,
+                       adv_inv_std, d_adv_stats, d_grad, stream, mode, obs_stride);
 }
 
 extern "C" int dronecu_ppo_debug_buffer(dronecu_ppo* p, float* d_dbg) {

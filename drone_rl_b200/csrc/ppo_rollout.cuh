@@ -119,7 +119,8 @@ struct PolicyArgs {
   uint64_t t0;
   const float* theta;     // [kParams]
   int32_t deterministic;  // != 0: action = mean (SB3 predict(deterministic=True), test.py:14)
-  float* obs;             // [K,n,15] observation the action was computed from
+  float* obs;             // [K,n,15] observation the action was computed from ([K,n,16] when obs_padded)
+  int32_t obs_padded;     // != 0: rows padded to 16 floats (64 bytes, the 16th = 1.0: the bias column of the update kernels' X tile)
   float4* actions;        // [K,n]    sampled action, NOT clipped (what SB3 stores in the buffer)
   float* logp;            // [K,n]
   float* value;           // [K,n]
@@ -174,7 +175,15 @@ __global__ void __launch_bounds__(kPolBlock) policy_rollout_kernel(const __grid_
   for (int k = 0; k < A.K; ++k) {
     float x[kObs];
     write_obs<kObs>(x, s);
-    if (A.obs != nullptr && valid > 0) emit_obs_rows<kObs>(tile, p_obs, s, lane, valid, active, fast_obs);
+    if (A.obs != nullptr && A.obs_padded) {        // 64-byte rows: four 128-bit stores straight from the registers
+      if (active) {
+        float4* d = reinterpret_cast<float4*>(A.obs + ((size_t)k * (size_t)n + (size_t)i) * 16);
+        st_quad(d, make_float4(x[0], x[1], x[2], x[3]));
+        st_quad(d + 1, make_float4(x[4], x[5], x[6], x[7]));
+        st_quad(d + 2, make_float4(x[8], x[9], x[10], x[11]));
+        st_quad(d + 3, make_float4(x[12], x[13], x[14], 1.0f));
+      }
+    } else if (A.obs != nullptr && valid > 0) emit_obs_rows<kObs>(tile, p_obs, s, lane, valid, active, fast_obs);
 
     float mean[kAct], val[1];
     tower_forward<kAct>(S, 0, x, mean);

@@ -75,7 +75,15 @@ __global__ void __launch_bounds__(tc::kTile) policy_rollout_tc_kernel(const __gr
   for (int k = 0; k < A.K; ++k) {
     float x[kObs];
     write_obs<kObs>(x, s);
-    if (A.obs != nullptr && valid > 0) emit_obs_rows<kObs>(tile, p_obs, s, lane, valid, active, fast_obs);
+    if (A.obs != nullptr && A.obs_padded) {        // 64-byte rows: four 128-bit stores straight from the registers
+      if (active) {
+        float4* d = reinterpret_cast<float4*>(A.obs + ((size_t)k * (size_t)n + (size_t)i) * 16);
+        st_quad(d, make_float4(x[0], x[1], x[2], x[3]));
+        st_quad(d + 1, make_float4(x[4], x[5], x[6], x[7]));
+        st_quad(d + 2, make_float4(x[8], x[9], x[10], x[11]));
+        st_quad(d + 3, make_float4(x[12], x[13], x[14], 1.0f));
+      }
+    } else if (A.obs != nullptr && valid > 0) emit_obs_rows<kObs>(tile, p_obs, s, lane, valid, active, fast_obs);
 
     float mean[kAct], val;
     tc::forward(S, x, phase, mean, val);

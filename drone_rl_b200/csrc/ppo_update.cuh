@@ -35,7 +35,8 @@ struct UpdSmem {
 
 struct UpdArgs {
   const float* theta;        // [kParams]
-  const float* obs;          // [B,15]
+  const float* obs;          // [B,15] ([B,16] rows of 64 bytes, 16th value 1.0, when obs_stride == 16)
+  int obs_stride;            // floats per observation row: 15 or 16
   const float4* actions;     // [B]
   const float* old_logp;     // [B]
   const float* adv;          // [B]
@@ -275,7 +276,7 @@ __global__ void __launch_bounds__(kUpdBlock, 1) ppo_grad_kernel(const __grid_con
 
     float x[kObs];
 #pragma unroll
-    for (int i = 0; i < kObs; ++i) x[i] = live ? A.obs[row * kObs + i] : 0.f;
+    for (int i = 0; i < kObs; ++i) x[i] = live ? A.obs[row * A.obs_stride + i] : 0.f;
 #pragma unroll
     for (int q = 0; q < 4; ++q)
       reinterpret_cast<float4*>(U.bufX[tid])[q] =

@@ -404,7 +404,7 @@ __global__ void __launch_bounds__(tcu::kThreads, 1) ppo_grad_tc_kernel(const __g
         // always a valid address: rows past the end of the minibatch read row 0 and are zeroed when staged, so all
         // 16 loads are in flight at once (a select on the loaded value made ptxas serialise them in v2.1)
         const int rr = max(__shfl_sync(0xffffffffu, row32, 2 * p + half), 0);
-        asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(in.xe[p]) : "l"(A.obs + (int64_t)rr * kObs + col));
+        asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(in.xe[p]) : "l"(A.obs + (int64_t)rr * A.obs_stride + col));
       }
       in.act = make_float4(0.f, 0.f, 0.f, 0.f);
       in.old_logp = in.adv_raw = in.ret = 0.f;

@@ -254,6 +254,10 @@ __device__ __forceinline__ void issuer_accum(Smem3& S, const int n_cta, long lon
 constexpr size_t kTc3Smem = sizeof(tcb::Smem3) + 1024;
 
 // partials: [2 towers][gridDim.x][kGradLen]
+// PADDED: the observation rows are 64 bytes (16 floats, the 16th = 1.0: dronecu_policy_out.obs_padded) -- a row is four aligned
+// 16-byte chunks, fetched as LDG.128 by four lanes (8 rows per load instruction instead of 2) and staged with one STS.128 (tf32 X
+// tile: four consecutive k of a sample are contiguous) + one STS.64 (bf16 X) per chunk instead of eight 4- / 2-byte stores.
+template <bool PADDED>
 __global__ void __launch_bounds__(tcb::kThreads3, 1) ppo_grad_bf16_kernel(const __grid_constant__ UpdArgs A) {
   using namespace tcb;
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
@@ -348,6 +352,12 @@ __global__ void __launch_bounds__(tcb::kThreads3, 1) ppo_grad_bf16_kernel(const 
     // tile overflow the SM's outstanding-miss capacity and the load ISSUE stalled for 3-4k of 15k cycles per tile (in-kernel
     // timeline at the c5 size, profiles/r02_grad_timeline_sorted_rows_c5_size.txt).
     auto gather_rows = [&](int row32, RowIn& in, const int p0) {      // observation rows: 4 of the 16 two-row loads
+      if constexpr (PADDED) {       // part p0 / 4: samples 8 (p0 / 4) + (lane >> 2) of this warp, chunk lane & 3 of their rows
+        const int rr = max(__shfl_sync(0xffffffffu, row32, 2 * p0 + (lane >> 2)), 0);
+        asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(in.xe[p0]), "=f"(in.xe[p0 + 1]), "=f"(in.xe[p0 + 2]), "=f"(in.xe[p0 + 3])
+                     : "l"(A.obs + (int64_t)rr * 16 + 4 * (lane & 3)));
+        return;
+      }
       const int col = min(lane & 15, kObs - 1), half = lane >> 4;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
@@ -392,6 +402,22 @@ __global__ void __launch_bounds__(tcb::kThreads3, 1) ppo_grad_bf16_kernel(const 
       __syncwarp();
       TSTAMP(tlog, it, 1);
       // ---------------- X -> shared memory: tf32 [samples x 16] (A of S1) and bf16 MN-major (B of S6) ----------------
+      if constexpr (PADDED) {
+        const uint32_t live_all = __ballot_sync(0xffffffffu, live);
+        const int j = lane & 3;
+        unsigned char* const xnb = XN0 + (it & 1) * (2 * kGrp) + (j >> 1) * kGrp + (j & 1) * 8;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int sl = 8 * q + (lane >> 2), m = 32 * wq + sl;               // sample within the warp / within the tile
+          const bool on = (live_all >> sl) & 1u;
+          float4 v = make_float4(cur.xe[4 * q], cur.xe[4 * q + 1], cur.xe[4 * q + 2], cur.xe[4 * q + 3]);
+          if (j == 3) v.w = 1.0f;                                            // the bias column, whatever the buffer holds
+          if (!on) v = make_float4(0.f, 0.f, 0.f, 0.f);
+          *reinterpret_cast<float4*>(XS + (m >> 3) * kXsSbo + j * kXsLbo + ((m & 7) << 4)) =
+              make_float4(to_tf32_fast(v.x), to_tf32_fast(v.y), to_tf32_fast(v.z), to_tf32_fast(v.w));
+          *reinterpret_cast<uint2*>(xnb + m * 16) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+        }
+      } else
       {
         const int col = lane & 15, half = lane >> 4, base = 32 * wq + half;
         const uint32_t live_mask = __ballot_sync(0xffffffffu, live) >> half;

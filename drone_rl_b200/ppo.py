@@ -80,11 +80,15 @@ def unpack_params(flat: torch.Tensor) -> dict:
 
 
 class RolloutBuffers:
-    """Device-resident rollout buffers [K, n, ...] (SB3 RolloutBuffer)."""
+    """Device-resident rollout buffers [K, n, ...] (SB3 RolloutBuffer).  ``obs`` is always the [K, n, 15] view; with
+    ``padded_obs`` the storage behind it (``obs_store``) has 64-byte rows [K, n, 16] whose 16th value the rollout kernel
+    writes as 1.0 -- four aligned 16-byte chunks per row for the update kernel's gathers."""
 
-    def __init__(self, K, n, device):
+    def __init__(self, K, n, device, padded_obs: bool = False):
         f = dict(dtype=torch.float32, device=device)
-        self.obs = torch.empty(K, n, 15, **f)
+        self.obs_stride = 16 if padded_obs else 15
+        self.obs_store = torch.empty(K, n, self.obs_stride, **f)
+        self.obs = self.obs_store[..., :15]
         self.actions = torch.empty(K, n, 4, **f)
         self.logp = torch.empty(K, n, **f)
         self.value = torch.empty(K, n, **f)
@@ -109,7 +113,7 @@ class PPO:
                  max_grad_norm: float = 0.5, learning_rate: float = 3e-4, normalize_advantage: bool = True,
                  seed: int = 0, device: int = 0, verbose: int = 0, policy_seed: Optional[int] = None,
                  rollout_precision: str = "fp32", update_precision: str = "fp32", cuda_graph: Optional[bool] = None,
-                 dp_backend: str = "peer"):
+                 dp_backend: str = "peer", padded_obs: Optional[bool] = None):
         self.lib = _lib.load()
         self.rank, self.world = 0, 1
         if torch.distributed.is_available() and torch.distributed.is_initialized():
@@ -138,7 +142,10 @@ class PPO:
         _lib.check(self.lib.dronecu_ppo_create(C.byref(cfg), self.device.index, C.byref(h)), "dronecu_ppo_create")
         self._h = h
         self.params = init_policy_params(seed if policy_seed is None else policy_seed).to(self.device)
-        self.buf = RolloutBuffers(n_steps, self.n_envs, self.device)
+        # 64-byte observation rows in the rollout buffer: default for the bf16 update kernel (its gathers and X staging are
+        # vectorised for them); every kernel accepts either layout
+        self.padded_obs = (update_precision == "bf16") if padded_obs is None else bool(padded_obs)
+        self.buf = RolloutBuffers(n_steps, self.n_envs, self.device, self.padded_obs)
         self._grad = torch.zeros(GRAD_LEN, dtype=torch.float32, device=self.device)
         self._adv_stats = torch.zeros(3, dtype=torch.float64, device=self.device)
         self._info = torch.zeros(9, dtype=torch.float32, device=self.device)
@@ -247,8 +254,8 @@ class PPO:
     def collect_rollouts(self, deterministic: bool = False):
         """One launch: n_steps env steps for every env, policy evaluated in-kernel; then GAE."""
         b, K, n = self.buf, self.n_steps, self.n_envs
-        out = PolicyOut(b.obs.data_ptr(), b.actions.data_ptr(), b.logp.data_ptr(), b.value.data_ptr(),
-                        b.reward.data_ptr(), b.done.data_ptr(), b.last_value.data_ptr(), None)
+        out = PolicyOut(b.obs_store.data_ptr(), b.actions.data_ptr(), b.logp.data_ptr(), b.value.data_ptr(),
+                        b.reward.data_ptr(), b.done.data_ptr(), b.last_value.data_ptr(), None, int(self.padded_obs), 0)
         st = _stream_ptr(self.device)
         fn = self.lib.dronecu_rollout_policy_tc if self.rollout_precision == "tf32" else self.lib.dronecu_rollout_policy
         _lib.check(fn(self.batch._h, K, _ptr(self.params), int(deterministic), C.byref(out), st), "dronecu_rollout_policy")
@@ -273,14 +280,10 @@ class PPO:
             self._allreduce_f64(self._adv_stats)
             stats_ptr = _ptr(self._adv_stats)
             self.launches += 2
-        grad_fn = {"fp32": self.lib.dronecu_ppo_grad, "tf32": self.lib.dronecu_ppo_grad_tc,
-                   "bf16": self.lib.dronecu_ppo_grad_bf16}[self.update_precision]
         if self.grad_events is not None:          # bench.py: CUDA events around the gradient launches
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), m)
             ev[0].record()
-        _lib.check(grad_fn(self._h, _ptr(self.params), _ptr(b.obs), _ptr(b.actions), _ptr(b.logp),
-                           _ptr(b.adv), _ptr(b.ret), _ptr(index), first, m, 0.0, 1.0, stats_ptr,
-                           _ptr(self._grad), st), "dronecu_ppo_grad")
+        self.launch_grad(index, first, m, stats_ptr, self._grad)
         if self.grad_events is not None:
             ev[1].record()
             self.grad_events.append(ev)
@@ -296,6 +299,17 @@ class PPO:
                                                   1.0 / (m * self.world), _ptr(self._info), st), "dronecu_ppo_apply")
         self.launches += 3
         self.n_updates += 1
+
+    def launch_grad(self, index: Optional[torch.Tensor], first: int, m: int, stats_ptr, grad: torch.Tensor,
+                    precision: Optional[str] = None):
+        """One launch of the minibatch-gradient kernel (+ its fixed-order reduce) over this model's rollout buffers: rows
+        ``index[0:m]`` (or ``first .. first+m``), advantage statistics from ``stats_ptr`` (a ctypes pointer to [sum, sumsq,
+        count] or None: no normalisation), result in ``grad`` [GRAD_LEN]."""
+        b = self.buf
+        mode = {"fp32": 0, "tf32": 1, "bf16": 2}[precision or self.update_precision]
+        _lib.check(self.lib.dronecu_ppo_grad_strided(self._h, mode, b.obs_stride, _ptr(self.params), _ptr(b.obs_store), _ptr(b.actions),
+                                                     _ptr(b.logp), _ptr(b.adv), _ptr(b.ret), _ptr(index), first, m, 0.0, 1.0,
+                                                     stats_ptr, _ptr(grad), _stream_ptr(self.device)), "dronecu_ppo_grad")
 
     def _epoch_graph(self, perm: torch.Tensor, B: int, ep_stats: Optional[torch.Tensor] = None):
         """Replay (capture on first use) the CUDA graph of one epoch over the index buffer `perm`."""

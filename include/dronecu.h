@@ -201,6 +201,9 @@ typedef struct dronecu_policy_out {
   uint8_t* d_done;     /* [K,n]    episode ended at step k (== episode_start of step k+1)                 */
   float* d_last_value; /* [n]      V(observation after the K-th step), the GAE bootstrap                  */
   float* d_last_obs;   /* [n,15]   that observation                                                       */
+  int32_t obs_padded;  /* != 0: d_obs rows are 64 bytes -- [K,n,16], the 16th value written as 1.0 (the bias column of the
+                          update kernels' X tile); pass the buffer to dronecu_ppo_grad_strided with obs_stride 16          */
+  int32_t reserved;
 } dronecu_policy_out;
 
 /* SB3 collect_rollouts for K steps in ONE launch: per step a,v,logp = policy(obs); env.step(clip(a));
@@ -296,6 +299,15 @@ int dronecu_ppo_grad_bf16(dronecu_ppo* ppo, const float* d_params, const float* 
                           const float* d_old_logp, const float* d_adv, const float* d_returns, const int32_t* d_index,
                           int64_t first, int64_t m, float adv_mean, float adv_inv_std, const double* d_adv_stats,
                           float* d_grad, void* stream);
+
+/* The three gradient kernels behind one entry point, with the row stride of d_obs: mode 0 = dronecu_ppo_grad (fp32), 1 =
+ * dronecu_ppo_grad_tc, 2 = dronecu_ppo_grad_bf16; obs_stride 15 = packed rows (what the entry points above assume), 16 = the
+ * 64-byte rows dronecu_rollout_policy[_tc] writes with obs_padded (16-byte aligned; the bf16 kernel then fetches a row as four
+ * 128-bit chunks and stages it with vector stores). */
+int dronecu_ppo_grad_strided(dronecu_ppo* ppo, int mode, int obs_stride, const float* d_params, const float* d_obs,
+                             const float* d_actions, const float* d_old_logp, const float* d_adv, const float* d_returns,
+                             const int32_t* d_index, int64_t first, int64_t m, float adv_mean, float adv_inv_std,
+                             const double* d_adv_stats, float* d_grad, void* stream);
 
 /* Debugging aid for dronecu_ppo_grad_tc: when d_dbg is not NULL the next calls also dump the raw TMEM image
  * of every warpgroup, float32 [2 * grid.x, 128 lanes, 256 columns] (policy-tower CTAs; grid.x = min(ceil(tiles / 2), SMs / 2)) (grid = min(ceil(tiles / 2), SM count)). */

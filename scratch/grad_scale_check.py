@@ -26,13 +26,13 @@ print("adv stats", stats.cpu().numpy())
 def grad(fn, k):
     g = torch.zeros(_lib.GRAD_LEN, device="cuda")
     idx = perm[k * m:(k + 1) * m]
-    _lib.check(fn(model._h, P(model.params), P(b.obs), P(b.actions), P(b.logp), P(b.adv), P(b.ret), P(idx), 0, m, 0.0, 1.0, P(stats[k]), P(g), None))
+    model.launch_grad(idx, 0, m, P(stats[k]), g, precision=fn)
     torch.cuda.synchronize()
     return g.cpu().numpy()
 for k in range(mb):
-    g16 = grad(model.lib.dronecu_ppo_grad_bf16, k)
-    g16b = grad(model.lib.dronecu_ppo_grad_bf16, k)
-    g32 = grad(model.lib.dronecu_ppo_grad, k)
+    g16 = grad("bf16", k)
+    g16b = grad("bf16", k)
+    g32 = grad("fp32", k)
     bad = ~np.isfinite(g16)
     scale = np.abs(g32[:10697]).max()
     print(f"minibatch {k}: bf16 non-finite entries {bad.sum()} at {np.flatnonzero(bad)[:8]}, reproducible {np.array_equal(g16, g16b, equal_nan=True)}, "

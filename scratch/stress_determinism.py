@@ -42,7 +42,7 @@ for name, fn, r in kernels:
     g = torch.zeros(_lib.GRAD_LEN, device="cuda")
     for i in range(r):
         k = i % mb
-        _lib.check(fn(A._h, P(A.params), P(b.obs), P(b.actions), P(b.logp), P(b.adv), P(b.ret), P(perm0[k * m:(k + 1) * m]), 0, m, 0.0, 1.0, P(stats0[k]), P(g), None))
+        A.launch_grad(perm0[k * m:(k + 1) * m], 0, m, P(stats0[k]), g, precision=name)
         if ref[k] is None:
             ref[k] = g.clone()
         elif not torch.equal(g, ref[k]):

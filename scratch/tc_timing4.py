@@ -21,7 +21,7 @@ idx = idx.to(torch.int32)
 for rep in range(2):
     dbg.zero_(); model._adv_stats.zero_()
     _lib.check(model.lib.dronecu_ppo_adv_stats(model._h, P(b.adv), P(idx), 0, m, P(model._adv_stats), None))
-    _lib.check(model.lib.dronecu_ppo_grad_bf16(model._h, P(model.params), P(b.obs), P(b.actions), P(b.logp), P(b.adv), P(b.ret), P(idx), 0, m, 0.0, 1.0, P(model._adv_stats), P(model._grad), None))
+    model.launch_grad(idx, 0, m, P(model._adv_stats), model._grad)
     torch.cuda.synchronize()
 t = dbg.cpu().numpy().view(np.int64)
 names = ["top", "w(S6p)", "h1", "gath", "wS1", "h2", "wS2", "h3", "wS3", "h4", "wS4", "h5", "wS5", "h6"]
