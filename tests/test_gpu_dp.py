@@ -226,3 +226,52 @@ def test_all_ranks_hold_identical_replicas(drl):
     out = _run_dp("peer", "bf16", world=world)
     assert out["identical"] and out["graph"]
     assert torch.isfinite(out["params"]).all()
+
+
+def _ckpt_worker(rank, world, port, path, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import drone_rl_b200 as drl
+    from drone_rl_b200.ppo import PPO
+    n = 512
+    mk = lambda: drl.DroneBatch(n, drl.EnvConfig.single(), device=rank, seed=9, env_offset=rank * n)
+    a = PPO(mk(), n_steps=16, batch_size=n * 16 // 2, n_epochs=1, seed=9)
+    a.learn(3 * n * 16 * world)
+    a.save(path)                                    # rank 0: the archive; rank 1: its env shard next to it
+    dist.barrier()
+    b = PPO.load(path, mk(), n_steps=16, batch_size=n * 16 // 2, n_epochs=1)
+    sa, sb = a.batch.get_state(), b.batch.get_state()
+    out = {"restored": bool(b.env_state_restored),
+           "env_equal": all(np.array_equal(sa[k], sb[k], equal_nan=True) for k in sa),
+           "params_equal": bool(torch.equal(a.params, b.params)),
+           "first_pos": sa["pos"][0].tolist(), "step": (a.batch.global_step, b.batch.global_step)}
+    gathered = [None] * world
+    dist.all_gather_object(gathered, out)
+    a.close(); b.close()
+    if rank == 0:
+        q.put(gathered)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+def test_data_parallel_checkpoint_restores_every_ranks_own_shard(drl, tmp_path):
+    """rank 0's archive holds rank 0's env shard only -- on resume every rank must get ITS OWN env / curriculum / RNG
+    state back (side files next to the archive), not a copy of shard 0; policy and Adam state are the replicas."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q, port, path = ctx.Queue(), _free_port(), str(tmp_path / "dp_ckpt")
+    procs = [ctx.Process(target=_ckpt_worker, args=(r, 2, port, path, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert os.path.isfile(path + ".zip") and os.path.isfile(path + ".env.rank1.pt")
+    for r, o in enumerate(res):
+        assert o["restored"] and o["env_equal"] and o["params_equal"], (r, o)
+        assert o["step"][0] == o["step"][1]
+    assert res[0]["first_pos"] != res[1]["first_pos"]          # the two shards really differ
