@@ -244,11 +244,12 @@ extern "C" int dronecu_minibatch_partition(dronecu_ppo* p, int64_t n, int64_t ba
   }
   const unsigned grid = (n_chunks + kPartWarps - 1) / kPartWarps;
   cudaStream_t st = (cudaStream_t)stream;
-  part_hist_kernel<<<grid, 32 * kPartWarps, 0, st>>>((uint32_t)n, (uint32_t)batch, (uint32_t)n_bins, rows_per_warp, n_chunks, K, p->part_hist);
+  const FastDiv fd = fast_div_make((uint32_t)batch);
+  part_hist_kernel<<<grid, 32 * kPartWarps, 0, st>>>((uint32_t)n, fd, (uint32_t)n_bins, rows_per_warp, n_chunks, K, p->part_hist);
   CUDA_TRY(cudaGetLastError());
   part_scan_kernel<<<1, 1024, 0, st>>>(p->part_hist, (uint32_t)len);
   CUDA_TRY(cudaGetLastError());
-  part_scatter_kernel<<<grid, 32 * kPartWarps, 0, st>>>((uint32_t)n, (uint32_t)batch, (uint32_t)n_bins, rows_per_warp, n_chunks, K, p->part_hist, d_out);
+  part_scatter_kernel<<<grid, 32 * kPartWarps, 0, st>>>((uint32_t)n, fd, (uint32_t)n_bins, rows_per_warp, n_chunks, K, p->part_hist, d_out);
   CUDA_TRY(cudaGetLastError());
   p->launches += 3;
   return DRONECU_OK;

@@ -563,11 +563,32 @@ __global__ void perm_kernel(int32_t* __restrict__ out, uint32_t n, const __grid_
 constexpr int kPartMaxBins = 64;
 constexpr int kPartWarps = 8;
 
-__device__ __forceinline__ uint32_t part_key(uint32_t r, const PermKey& K, uint32_t n, uint32_t batch) {
-  return perm_apply(r, K, n) / batch;
+// x / d for an invariant 32-bit divisor (Granlund-Montgomery: q = (t + ((x - t) >> s1)) >> s2 with t = umulhi(M, x)); a hardware-free
+// 32-bit division is ~15 instructions, this is 5 -- the partition kernels divide once per buffer row
+struct FastDiv { uint32_t M, s1, s2; };
+inline FastDiv fast_div_make(uint32_t d) {
+  FastDiv f;
+  uint32_t l = 0;
+  while ((1ull << l) < d) ++l;                                   // l = ceil(log2 d)
+  f.M = (uint32_t)(((1ull << 32) * ((1ull << l) - d)) / d + 1);
+  f.s1 = l < 1 ? l : 1u;
+  f.s2 = l < 1 ? 0u : l - 1;
+  return f;
+}
+__host__ __device__ __forceinline__ uint32_t fast_div(uint32_t x, const FastDiv& f) {
+#ifdef __CUDA_ARCH__
+  const uint32_t t = __umulhi(f.M, x);
+#else
+  const uint32_t t = (uint32_t)(((uint64_t)f.M * x) >> 32);
+#endif
+  return (t + ((x - t) >> f.s1)) >> f.s2;
 }
 
-__global__ void __launch_bounds__(32 * kPartWarps) part_hist_kernel(uint32_t n, uint32_t batch, uint32_t n_bins, uint32_t rows_per_warp,
+__device__ __forceinline__ uint32_t part_key(uint32_t r, const PermKey& K, uint32_t n, const FastDiv& batch) {
+  return fast_div(perm_apply(r, K, n), batch);
+}
+
+__global__ void __launch_bounds__(32 * kPartWarps) part_hist_kernel(uint32_t n, FastDiv batch, uint32_t n_bins, uint32_t rows_per_warp,
                                                                    uint32_t n_chunks, const __grid_constant__ PermKey K, uint32_t* __restrict__ H) {
   __shared__ uint32_t hist[kPartWarps][kPartMaxBins];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -589,37 +610,50 @@ __global__ void __launch_bounds__(32 * kPartWarps) part_hist_kernel(uint32_t n, 
 }
 
 __global__ void __launch_bounds__(1024) part_scan_kernel(uint32_t* __restrict__ H, uint32_t len) {
-  // one CTA walks H in tiles of 1024 consecutive elements (coalesced), a shuffle scan per warp + a scan of the 32 warp totals
-  // per tile, a running carry across the tiles
+  // one CTA walks H in tiles of 1024 consecutive elements (coalesced): a shuffle scan per warp + a scan of the 32 warp totals
+  // per tile, a running carry across the tiles.  The loads of 16 tiles are issued together (one memory round trip per 16 tiles
+  // instead of one per tile: the tile loop is a dependent chain).
   __shared__ uint32_t wsum[32];
   __shared__ uint32_t carry_s;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) carry_s = 0;
   __syncthreads();
-  for (uint32_t base = 0; base < len; base += 1024) {
-    const uint32_t i = base + threadIdx.x;
-    const uint32_t v = i < len ? H[i] : 0u;
-    uint32_t incl = v;
+  constexpr int kAhead = 16;
+  for (uint32_t base0 = 0; base0 < len; base0 += 1024 * kAhead) {
+    uint32_t vals[kAhead];
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (uint32_t)o) incl += t; }
-    if (lane == 31) wsum[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-      uint32_t w = wsum[lane];
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= (uint32_t)o) w += t; }
-      wsum[lane] = w;                                   // inclusive scan of the warp totals
+    for (int t = 0; t < kAhead; ++t) {
+      const uint32_t i = base0 + 1024 * t + threadIdx.x;
+      vals[t] = i < len ? H[i] : 0u;
     }
-    __syncthreads();
-    const uint32_t carry = carry_s;
-    if (i < len) H[i] = carry + (warp ? wsum[warp - 1] : 0u) + incl - v;        // exclusive prefix
-    __syncthreads();
-    if (threadIdx.x == 0) carry_s = carry + wsum[31];
-    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < kAhead; ++t) {
+      const uint32_t base = base0 + 1024 * t;
+      if (base >= len) break;
+      const uint32_t i = base + threadIdx.x;
+      const uint32_t v = vals[t];
+      uint32_t incl = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (uint32_t)o) incl += u; }
+      if (lane == 31) wsum[warp] = incl;
+      __syncthreads();
+      if (warp == 0) {
+        uint32_t w = wsum[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, w, o); if (lane >= (uint32_t)o) w += u; }
+        wsum[lane] = w;                                   // inclusive scan of the warp totals
+      }
+      __syncthreads();
+      const uint32_t carry = carry_s;
+      if (i < len) H[i] = carry + (warp ? wsum[warp - 1] : 0u) + incl - v;        // exclusive prefix
+      __syncthreads();
+      if (threadIdx.x == 0) carry_s = carry + wsum[31];
+      __syncthreads();
+    }
   }
 }
 
-__global__ void __launch_bounds__(32 * kPartWarps) part_scatter_kernel(uint32_t n, uint32_t batch, uint32_t n_bins, uint32_t rows_per_warp,
+__global__ void __launch_bounds__(32 * kPartWarps) part_scatter_kernel(uint32_t n, FastDiv batch, uint32_t n_bins, uint32_t rows_per_warp,
                                                                       uint32_t n_chunks, const __grid_constant__ PermKey K,
                                                                       const uint32_t* __restrict__ H, int32_t* __restrict__ out) {
   __shared__ uint32_t base[kPartWarps][kPartMaxBins];
