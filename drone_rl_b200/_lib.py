@@ -105,6 +105,7 @@ _SIGNATURES = {
     # PPO half
     "dronecu_rollout_policy": (C.c_int, [_P, C.c_int, _P, C.c_int, C.POINTER(PolicyOut), _P]),
     "dronecu_policy_forward": (C.c_int, [C.c_int, C.c_int64, _P, _P, _P, _P, _P]),
+    "dronecu_set_rollout_kernel": (C.c_int, [C.c_int]),
     "dronecu_rollout_policy_tc": (C.c_int, [_P, C.c_int, _P, C.c_int, C.POINTER(PolicyOut), _P]),
     "dronecu_policy_forward_tc": (C.c_int, [C.c_int, C.c_int64, _P, _P, _P, _P, _P, _P, _P]),
     "dronecu_gae": (C.c_int, [C.c_int, C.c_int, C.c_int64, _P, _P, _P, _P, C.c_float, C.c_float, _P, _P, _P]),

@@ -40,6 +40,17 @@ struct dronecu_ppo {
   bool dp_opened[kDpMaxWorld];   // mail[r] was mapped with cudaIpcOpenMemHandle (to be closed)
 };
 
+// 0 = automatic (one warp per env up to kWarpRolloutMaxEnvs envs, one thread per env above), 1 = always one thread per env,
+// 2 = always one warp per env: dronecu_set_rollout_kernel (tests pin each kernel against the oracle)
+static int g_rollout_kernel_mode = 0;
+constexpr int64_t kWarpRolloutMaxEnvs = 4096;
+
+extern "C" int dronecu_set_rollout_kernel(int mode) {
+  if (mode < 0 || mode > 2) return fail(DRONECU_ERR_INVALID, "dronecu_set_rollout_kernel: mode must be 0 (auto), 1 (thread per env) or 2 (warp per env)");
+  g_rollout_kernel_mode = mode;
+  return DRONECU_OK;
+}
+
 static int rollout_policy_impl(dronecu_env* e, int K, const float* d_params, int deterministic,
                                const dronecu_policy_out* out, void* stream, bool tensor_cores) {
   if (!e || !d_params) return fail(DRONECU_ERR_INVALID, "dronecu_rollout_policy: null argument");
@@ -71,6 +82,16 @@ static int rollout_policy_impl(dronecu_env* e, int K, const float* d_params, int
     } else {
       CUDA_TRY(cudaFuncSetAttribute(policy_rollout_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
       policy_rollout_tc_kernel<false><<<grid, tc::kTile, kTcSmem, st>>>(a);
+    }
+  } else if (g_rollout_kernel_mode == 2 || (g_rollout_kernel_mode == 0 && e->n <= kWarpRolloutMaxEnvs)) {
+    // small batches: one warp per env (ppo_rollout.cuh)
+    const unsigned gw = (unsigned)((e->n + kSmallWarps - 1) / kSmallWarps);
+    if (e->cfg.flags & DRONECU_RANDOMIZED) {
+      CUDA_TRY(cudaFuncSetAttribute(policy_rollout_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPolicySmallSmem));
+      policy_rollout_warp_kernel<true><<<gw, 32 * kSmallWarps, kPolicySmallSmem, st>>>(a);
+    } else {
+      CUDA_TRY(cudaFuncSetAttribute(policy_rollout_warp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPolicySmallSmem));
+      policy_rollout_warp_kernel<false><<<gw, 32 * kSmallWarps, kPolicySmallSmem, st>>>(a);
     }
   } else if (e->cfg.flags & DRONECU_RANDOMIZED) {
     CUDA_TRY(cudaFuncSetAttribute(policy_rollout_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPolicySmem));

@@ -13,6 +13,12 @@ namespace dronecu {
 
 constexpr int kPolBlock = 128;
 
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
 // shared-memory image of the parameters, transposed to [in][out] so a thread walks the inputs of a
 // layer and fetches 4 output weights per LDS.128
 struct alignas(16) MlpSmem {
@@ -249,6 +255,158 @@ __global__ void __launch_bounds__(kPolBlock) policy_rollout_kernel(const __grid_
       atomicAdd(&blk_stats[1], (unsigned long long)n_term);
       atomicAdd(&blk_stats[2], (unsigned long long)len_sum);
       atomicAdd(&blk_ret, rs);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && blk_stats[0] != 0) {
+    StatSlot* slot = A.stats + (blockIdx.x % kStatSlots);
+    atomicAdd(&slot->episodes, blk_stats[0]);
+    atomicAdd(&slot->terminated, blk_stats[1]);
+    atomicAdd(&slot->length_sum, blk_stats[2]);
+    atomicAdd(&slot->return_sum, blk_ret);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Small batches (the reference's own shape is ONE env: train.py:33-43): one WARP per env.  With one env per thread a step
+// is a chain of ~10,000 dependent FMAs in a single thread (20 us per env step whatever the batch size below ~75k envs); here
+// the 64 hidden units of a layer are spread over the 32 lanes (units lane and lane + 32), the env state and the observation
+// are replicated in every lane (the env step is computed redundantly: no broadcast, no divergence), the activations of a
+// layer go through 256 bytes of shared memory per warp.  Same float32 arithmetic and the same fmaf order per hidden unit as
+// policy_rollout_kernel (layers 1 and 2 are bit-identical); the four / one head sums are warp reductions.
+// ---------------------------------------------------------------------------------------------
+constexpr int kSmallWarps = 4;                  // envs per CTA
+constexpr size_t kPolicySmallSmem = sizeof(MlpSmem) + sizeof(float) * kSmallWarps * kHid;
+
+template <int NOUT>
+__device__ __forceinline__ void tower_forward_warp(const MlpSmem& S, float* __restrict__ hbuf, const int t, const float (&x)[kObs],
+                                                   float (&out)[NOUT], const int lane) {
+  float a0 = S.b1[t][lane], a1 = S.b1[t][lane + 32];
+#pragma unroll
+  for (int i = 0; i < kObs; ++i) {
+    a0 = fmaf(S.W1T[t][i][lane], x[i], a0);
+    a1 = fmaf(S.W1T[t][i][lane + 32], x[i], a1);
+  }
+  a0 = tanh_fast(a0); a1 = tanh_fast(a1);
+  __syncwarp();                                 // the previous tower's readers of hbuf are done
+  hbuf[lane] = a0; hbuf[lane + 32] = a1;
+  __syncwarp();
+  float c0 = S.b2[t][lane], c1 = S.b2[t][lane + 32];
+#pragma unroll
+  for (int k4 = 0; k4 < kHid / 4; ++k4) {
+    const float4 h = reinterpret_cast<const float4*>(hbuf)[k4];          // warp-broadcast
+    c0 = fmaf(S.W2T[t][4 * k4][lane], h.x, c0);          c1 = fmaf(S.W2T[t][4 * k4][lane + 32], h.x, c1);
+    c0 = fmaf(S.W2T[t][4 * k4 + 1][lane], h.y, c0);      c1 = fmaf(S.W2T[t][4 * k4 + 1][lane + 32], h.y, c1);
+    c0 = fmaf(S.W2T[t][4 * k4 + 2][lane], h.z, c0);      c1 = fmaf(S.W2T[t][4 * k4 + 2][lane + 32], h.z, c1);
+    c0 = fmaf(S.W2T[t][4 * k4 + 3][lane], h.w, c0);      c1 = fmaf(S.W2T[t][4 * k4 + 3][lane + 32], h.w, c1);
+  }
+  c0 = tanh_fast(c0); c1 = tanh_fast(c1);
+  if constexpr (NOUT == kAct) {
+    const float4 w0 = reinterpret_cast<const float4*>(S.W3piT[lane])[0], w1 = reinterpret_cast<const float4*>(S.W3piT[lane + 32])[0];
+    out[0] = warp_sum(fmaf(w1.x, c1, w0.x * c0)) + S.b3pi[0];
+    out[1] = warp_sum(fmaf(w1.y, c1, w0.y * c0)) + S.b3pi[1];
+    out[2] = warp_sum(fmaf(w1.z, c1, w0.z * c0)) + S.b3pi[2];
+    out[3] = warp_sum(fmaf(w1.w, c1, w0.w * c0)) + S.b3pi[3];
+  } else {
+    out[0] = warp_sum(fmaf(S.W3vf[lane + 32], c1, S.W3vf[lane] * c0)) + S.b3vf;
+  }
+}
+
+template <bool RANDOMIZED>
+__global__ void __launch_bounds__(32 * kSmallWarps) policy_rollout_warp_kernel(const __grid_constant__ PolicyArgs A) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  MlpSmem& S = *reinterpret_cast<MlpSmem*>(smem_raw);
+  __shared__ unsigned long long blk_stats[3];
+  __shared__ double blk_ret;
+  load_mlp_smem(S, A.theta);
+  if (threadIdx.x < 3) blk_stats[threadIdx.x] = 0;
+  if (threadIdx.x == 3) blk_ret = 0.0;
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* const hbuf = reinterpret_cast<float*>(smem_raw + sizeof(MlpSmem)) + warp * kHid;
+  const int64_t i = (int64_t)blockIdx.x * kSmallWarps + warp;          // this warp's env
+  const bool active = i < A.n;                                            // warp-uniform
+  const EnvParams& P = A.P;
+  const uint64_t env_id = P.env_offset + (uint64_t)i;
+  const size_t n = (size_t)A.n;
+  const bool writer = active && lane == 0;
+
+  EnvState s = {};
+  if (active) s = load_state(A.state, i);                                 // every lane holds the whole state
+  float std_[kAct], logstd_sum = 0.f;
+#pragma unroll
+  for (int o = 0; o < kAct; ++o) { std_[o] = expf(S.log_std[o]); logstd_sum += S.log_std[o]; }
+  uint32_t n_done = 0, n_term = 0, len_sum = 0;
+  float ret_sum = 0.f;
+
+  for (int k = 0; k < A.K; ++k) {
+    float x[kObs];
+    write_obs<kObs>(x, s);
+    const size_t row = (size_t)k * n + (size_t)i;
+    if (writer && A.obs != nullptr) {
+      if (A.obs_padded) {
+        float4* d = reinterpret_cast<float4*>(A.obs + row * 16);
+        d[0] = make_float4(x[0], x[1], x[2], x[3]); d[1] = make_float4(x[4], x[5], x[6], x[7]);
+        d[2] = make_float4(x[8], x[9], x[10], x[11]); d[3] = make_float4(x[12], x[13], x[14], 1.0f);
+      } else {
+#pragma unroll
+        for (int c = 0; c < kObs; ++c) A.obs[row * kObs + c] = x[c];
+      }
+    }
+    float mean[kAct], val[1];
+    tower_forward_warp<kAct>(S, hbuf, 0, x, mean, lane);
+    tower_forward_warp<1>(S, hbuf, 1, x, val, lane);
+
+    float4 a;
+    float logp;
+    if (A.deterministic) {
+      a = make_float4(mean[0], mean[1], mean[2], mean[3]);
+      logp = -logstd_sum - kAct * kHalfLog2Pi;
+    } else {
+      const float4 z = noise_normals(P.keys, env_id, A.t0 + (uint64_t)k);
+      a = make_float4(fmaf(std_[0], z.x, mean[0]), fmaf(std_[1], z.y, mean[1]),
+                      fmaf(std_[2], z.z, mean[2]), fmaf(std_[3], z.w, mean[3]));
+      logp = -0.5f * (z.x * z.x + z.y * z.y + z.z * z.z + z.w * z.w) - logstd_sum - kAct * kHalfLog2Pi;
+    }
+    const float4 f = make_float4(fminf(fmaxf(a.x, 0.f), P.motor_max), fminf(fmaxf(a.y, 0.f), P.motor_max),
+                                 fminf(fmaxf(a.z, 0.f), P.motor_max), fminf(fmaxf(a.w, 0.f), P.motor_max));
+    const StepResult r = step_env(s, P, f);
+    const bool done = r.crashed || r.timeout;
+    if (writer) {
+      if (A.actions != nullptr) A.actions[row] = a;
+      if (A.logp != nullptr) A.logp[row] = logp;
+      if (A.value != nullptr) A.value[row] = val[0];
+      if (A.reward != nullptr) A.reward[row] = r.reward;
+      if (A.done != nullptr) A.done[row] = done ? 1 : 0;
+    }
+    if (active && done) {                                                 // warp-uniform
+      n_done += 1;
+      n_term += r.crashed ? 1 : 0;
+      len_sum += (uint32_t)s.ep_len;
+      ret_sum += s.ep_ret;
+      reset_env<RANDOMIZED>(s, P, env_id);
+    }
+  }
+  {
+    float x[kObs], val[1];
+    write_obs<kObs>(x, s);
+    if (A.last_value != nullptr) {
+      tower_forward_warp<1>(S, hbuf, 1, x, val, lane);
+      if (writer) A.last_value[i] = val[0];
+    }
+    if (writer && A.last_obs != nullptr) {
+#pragma unroll
+      for (int c = 0; c < kObs; ++c) A.last_obs[i * kObs + c] = x[c];
+    }
+  }
+  if (writer) {
+    store_state(A.state, i, s);
+    if (n_done != 0) {
+      atomicAdd(&blk_stats[0], (unsigned long long)n_done);
+      atomicAdd(&blk_stats[1], (unsigned long long)n_term);
+      atomicAdd(&blk_stats[2], (unsigned long long)len_sum);
+      atomicAdd(&blk_ret, (double)ret_sum);
     }
   }
   __syncthreads();

@@ -236,11 +236,6 @@ __device__ __forceinline__ void wgrad_head(UpdSmem& U, int w3off, int b3off, int
   }
 }
 
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
 
 __global__ void __launch_bounds__(kUpdBlock, 1) ppo_grad_kernel(const __grid_constant__ UpdArgs A) {
   extern __shared__ __align__(128) unsigned char smem_raw[];

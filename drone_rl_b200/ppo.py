@@ -257,7 +257,9 @@ class PPO:
         out = PolicyOut(b.obs_store.data_ptr(), b.actions.data_ptr(), b.logp.data_ptr(), b.value.data_ptr(),
                         b.reward.data_ptr(), b.done.data_ptr(), b.last_value.data_ptr(), None, int(self.padded_obs), 0)
         st = _stream_ptr(self.device)
-        fn = self.lib.dronecu_rollout_policy_tc if self.rollout_precision == "tf32" else self.lib.dronecu_rollout_policy
+        # tensor cores pay from ~1k envs (a tile is 128 envs; below that the float32 warp-per-env kernel is both faster and exact)
+        use_tc = self.rollout_precision == "tf32" and self.n_envs > 1024
+        fn = self.lib.dronecu_rollout_policy_tc if use_tc else self.lib.dronecu_rollout_policy
         _lib.check(fn(self.batch._h, K, _ptr(self.params), int(deterministic), C.byref(out), st), "dronecu_rollout_policy")
         _lib.check(self.lib.dronecu_gae(self.device.index, K, n, _ptr(b.reward), _ptr(b.value), _ptr(b.done),
                                         _ptr(b.last_value), self.gamma, self.gae_lambda, _ptr(b.adv), _ptr(b.ret), st),

@@ -72,13 +72,30 @@ def test_policy_forward(drl):
     model.close()
 
 
-def test_rollout_policy_record(drl):
+def lib_rejects_bad_mode():
+    from drone_rl_b200 import _lib
+    return _lib.load().dronecu_set_rollout_kernel(3) != 0
+
+
+@pytest.fixture
+def rollout_kernel_mode():
+    from drone_rl_b200 import _lib
+    lib = _lib.load()
+    yield lambda mode: _lib.check(lib.dronecu_set_rollout_kernel(mode))
+    lib.dronecu_set_rollout_kernel(0)
+
+
+@pytest.mark.parametrize("kernel", ["thread_per_env", "warp_per_env"])
+def test_rollout_policy_record(drl, rollout_kernel_mode, kernel):
     """Every recorded (obs, action, logp, value, reward, done) of an in-kernel-policy rollout is
-    reproduced by the oracle policy + Philox noise + the float64 env oracle, teacher-forced."""
+    reproduced by the oracle policy + Philox noise + the float64 env oracle, teacher-forced -- for both float32 kernels
+    (one thread per env: large batches; one warp per env: the default up to 4096 envs)."""
     from drone_rl_b200.ppo import PPO
     from drone_rl_b200._lib import PolicyOut
     import ctypes as C
     from drone_rl_b200 import _lib
+    rollout_kernel_mode({"thread_per_env": 1, "warp_per_env": 2}[kernel])
+    assert lib_rejects_bad_mode()
     n, K, seed = 3000, 40, 21
     model = PPO(drl.DroneBatch(n, drl.EnvConfig.single(), seed=seed, env_offset=77), n_steps=K, seed=seed)
     flat = _rand_params(5, scale=0.3)
@@ -119,7 +136,10 @@ def test_rollout_policy_record(drl):
     out2 = PolicyOut(b.obs.data_ptr(), b.actions.data_ptr(), b.logp.data_ptr(), None, None, None, None, None)
     _lib.check(model.lib.dronecu_rollout_policy(model.batch._h, 1, C.c_void_p(model.params.data_ptr()), 1, C.byref(out2), None))
     mean, _ = model.policy_forward(b.obs[0])
-    assert torch.equal(mean, b.actions[0])
+    if kernel == "thread_per_env":
+        assert torch.equal(mean, b.actions[0])
+    else:       # identical hidden layers; the four head sums are warp reductions instead of a 64-term fmaf chain
+        assert torch.allclose(mean, b.actions[0], rtol=0, atol=1e-5)
     model.close()
 
 
