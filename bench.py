@@ -46,6 +46,21 @@ MLP_FLOP = 20864.0                            # policy + value forward per env-s
 MOTOR_MAX = 7.3575
 
 
+def json_safe(o):
+    """Strict JSON has no NaN / Infinity: non-finite floats (an undefined explained variance, an empty episode mean) become null."""
+    if isinstance(o, float):
+        return o if np.isfinite(o) else None
+    if isinstance(o, (np.floating,)):
+        return float(o) if np.isfinite(o) else None
+    if isinstance(o, (np.integer,)):
+        return int(o)
+    if isinstance(o, dict):
+        return {k: json_safe(v) for k, v in o.items()}
+    if isinstance(o, (list, tuple)):
+        return [json_safe(v) for v in o]
+    return o
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     return json.load(open(p)) if os.path.isfile(p) else {}
@@ -369,7 +384,7 @@ def run_reference(args):
             sub = reference_ppo_line(args, w, cores) if w in ("c3", "c5") else reference_env_line(args, w, cores)
             extra[w] = {k: sub[k] for k in ("value", "unit", "ms_per_step", "steps", "dtype", "config", "cpu_baseline")}
         line["workloads"] = extra
-    print(json.dumps(line), flush=True)
+    print(json.dumps(json_safe(line), allow_nan=False), flush=True)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -779,7 +794,7 @@ def main():
         line.update({k: v for k, v in top.items() if k not in line})
         if extra:
             line["workloads"] = extra
-        print(json.dumps(line), flush=True)
+        print(json.dumps(json_safe(line), allow_nan=False), flush=True)
     ctx.close()
 
 
