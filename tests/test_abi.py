@@ -42,14 +42,14 @@ def test_struct_mirrors_match_header_sizes(lib, tmp_path):
     """Compile a tiny C program against include/dronecu.h and compare sizeof() with ctypes."""
     from drone_rl_b200 import _lib
     src = tmp_path / "sz.c"
-    src.write_text('#include <stdio.h>\n#include "dronecu.h"\nint main(){printf("%zu %zu %zu %zu %zu\\n",'
+    src.write_text('#include <stdio.h>\n#include "dronecu.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n",'
                    "sizeof(dronecu_config),sizeof(dronecu_rollout_out),sizeof(dronecu_step_out),"
-                   "sizeof(dronecu_state_view),sizeof(dronecu_stats));return 0;}\n")
+                   "sizeof(dronecu_state_view),sizeof(dronecu_stats),sizeof(dronecu_policy_out),sizeof(dronecu_ppo_config));return 0;}\n")
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     sizes = [int(x) for x in subprocess.check_output([str(exe)]).split()]
-    assert sizes[:5] == [C.sizeof(_lib.Config), C.sizeof(_lib.RolloutOut), C.sizeof(_lib.StepOut),
-                         C.sizeof(_lib.StateView), C.sizeof(_lib.Stats)]
+    assert sizes[:7] == [C.sizeof(_lib.Config), C.sizeof(_lib.RolloutOut), C.sizeof(_lib.StepOut),
+                         C.sizeof(_lib.StateView), C.sizeof(_lib.Stats), C.sizeof(_lib.PolicyOut), C.sizeof(_lib.PPOConfig)]
 
 
 def test_reference_defaults(lib):
