@@ -18,10 +18,14 @@
 //     S4..S6) in a FIXED order over the CTA's tiles (so that the accumulation order -- hence every bit of the result --
 //     does not depend on timing), software-pipelined over consecutive tiles: S4(j) S6(j-1) S5(j), so that the issuer
 //     serves another warpgroup while one computes dZ2 / dZ1.  The steps that only touch a warpgroup's private columns
-//     (S1..S3) need no order at all: warp 0 of each warpgroup issues them itself, right after the warpgroup's hand-over
-//     (it would only wait for their completion otherwise).  r02: before, one shared private-step issuer warp walked a
-//     global order, which made every warpgroup's S1 wait for another warpgroup's tanh phase -- 1.9k idle cycles per
-//     tile in the in-kernel timeline;
+//     (S1..S3) need no order at all: every warpgroup has its OWN private-step issuer warp (512 threads per CTA).  r02:
+//     before, one shared private-step issuer warp walked a global order, which made every warpgroup's S1 wait for
+//     another warpgroup's tanh phase -- 1.9k idle cycles per tile in the in-kernel timeline; issuing from warp 0 of the
+//     warpgroup instead (-DDRONECU_PRIVATE_ISSUER_WARPS=0) cost 9 %: that warp sits in the MMA issue for ~1k cycles when
+//     the tensor queue is full and becomes the straggler of its warpgroup;
+//   * the observation rows of the next tile are fetched a tile ahead in four parts spread over the tile; with 64-byte rows
+//     in the rollout buffer (template PADDED) a row is four LDG.128 by four lanes and is staged with vector stores; the tf32
+//     X tile is staged over the dead bufB (never over memory another warp still reads: the r02 race);
 //   * tanh'(layer 1) = 1 - H1^2 is stashed per sample as bf16 (2^-9 relative) next to the operands, because H1 itself
 //     survives only as a bf16 operand (1 - h^2 from a rounded h would lose the saturated units); tanh'(layer 2) uses
 //     the fp32 H2 still in TMEM.
