@@ -43,7 +43,7 @@ struct dronecu_ppo {
 // 0 = automatic (one warp per env up to kWarpRolloutMaxEnvs envs, one thread per env above), 1 = always one thread per env,
 // 2 = always one warp per env: dronecu_set_rollout_kernel (tests pin each kernel against the oracle)
 static int g_rollout_kernel_mode = 0;
-constexpr int64_t kWarpRolloutMaxEnvs = 4096;
+constexpr int64_t kWarpRolloutMaxEnvs = 8192;   // measured crossover ~12k envs (profiles/r02_rollout_kernel_sweep.txt)
 
 extern "C" int dronecu_set_rollout_kernel(int mode) {
   if (mode < 0 || mode > 2) return fail(DRONECU_ERR_INVALID, "dronecu_set_rollout_kernel: mode must be 0 (auto), 1 (thread per env) or 2 (warp per env)");

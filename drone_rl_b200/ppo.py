@@ -108,6 +108,8 @@ class PPO:
     ``batch_size`` counts samples PER RANK.
     """
 
+    tc_min_envs = 1024       # rollout_precision "tf32": tensor-core rollout kernel above this many envs per rank
+
     def __init__(self, env=1, n_steps: int = 2048, batch_size: int = 64, n_epochs: int = 10, gamma: float = 0.99,
                  gae_lambda: float = 0.95, clip_range: float = 0.2, ent_coef: float = 0.0, vf_coef: float = 0.5,
                  max_grad_norm: float = 0.5, learning_rate: float = 3e-4, normalize_advantage: bool = True,
@@ -258,7 +260,7 @@ class PPO:
                         b.reward.data_ptr(), b.done.data_ptr(), b.last_value.data_ptr(), None, int(self.padded_obs), 0)
         st = _stream_ptr(self.device)
         # tensor cores pay from ~1k envs (a tile is 128 envs; below that the float32 warp-per-env kernel is both faster and exact)
-        use_tc = self.rollout_precision == "tf32" and self.n_envs > 1024
+        use_tc = self.rollout_precision == "tf32" and self.n_envs > self.tc_min_envs
         fn = self.lib.dronecu_rollout_policy_tc if use_tc else self.lib.dronecu_rollout_policy
         _lib.check(fn(self.batch._h, K, _ptr(self.params), int(deterministic), C.byref(out), st), "dronecu_rollout_policy")
         _lib.check(self.lib.dronecu_gae(self.device.index, K, n, _ptr(b.reward), _ptr(b.value), _ptr(b.done),

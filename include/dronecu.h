@@ -213,7 +213,7 @@ int dronecu_rollout_policy(dronecu_env* env, int K, const float* d_params, int d
                            const dronecu_policy_out* out, void* stream);
 
 /* Which float32 kernel dronecu_rollout_policy launches: 0 = automatic (default: one WARP per env -- the hidden units of a layer
- * spread over the lanes -- up to 4096 envs, where a thread-per-env step is a 20 us chain of dependent FMAs; one THREAD per env
+ * spread over the lanes -- up to 8192 envs, where a thread-per-env step is a 20 us chain of dependent FMAs; one THREAD per env
  * above), 1 = always thread per env, 2 = always warp per env.  Process-wide; both kernels compute the same float32 arithmetic
  * (identical hidden layers, the head sums are warp reductions in the warp kernel). */
 int dronecu_set_rollout_kernel(int mode);
