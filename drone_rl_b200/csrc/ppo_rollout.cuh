@@ -72,8 +72,7 @@ __device__ __forceinline__ void tower_forward(const MlpSmem& S, const int t, con
 #pragma unroll
     for (int q = 0; q < kHid / 4; ++q) {
       const float4 w = reinterpret_cast<const float4*>(S.W1T[t][i])[q];
-      h1[4 * q] = fmaf(w.x, xi, h1[4 * q]); h1[4 * q + 1] = fmaf(w.y, xi, h1[4 * q + 1]);
-      h1[4 * q + 2] = fmaf(w.z, xi, h1[4 * q + 2]); h1[4 * q + 3] = fmaf(w.w, xi, h1[4 * q + 3]);
+      fma4s(h1 + 4 * q, w, xi);
     }
   }
 #pragma unroll
@@ -99,17 +98,14 @@ __device__ __forceinline__ void tower_forward(const MlpSmem& S, const int t, con
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const float4 w = reinterpret_cast<const float4*>(S.W2T[t][i] + 16 * c)[q];
-        acc[4 * q] = fmaf(w.x, hi, acc[4 * q]); acc[4 * q + 1] = fmaf(w.y, hi, acc[4 * q + 1]);
-        acc[4 * q + 2] = fmaf(w.z, hi, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(w.w, hi, acc[4 * q + 3]);
+        fma4s(acc + 4 * q, w, hi);
       }
     }
 #pragma unroll
     for (int jj = 0; jj < 16; ++jj) {
       const float a = tanh_fast(acc[jj]);
       if constexpr (NOUT == kAct) {
-        const float4 w = reinterpret_cast<const float4*>(S.W3piT[16 * c + jj])[0];
-        out[0] = fmaf(w.x, a, out[0]); out[1] = fmaf(w.y, a, out[1]);
-        out[2] = fmaf(w.z, a, out[2]); out[3] = fmaf(w.w, a, out[3]);
+        fma4s(out, reinterpret_cast<const float4*>(S.W3piT[16 * c + jj])[0], a);
       } else {
         out[0] = fmaf(S.W3vf[16 * c + jj], a, out[0]);
       }
@@ -270,7 +266,7 @@ __global__ void __launch_bounds__(kPolBlock) policy_rollout_kernel(const __grid_
 // ---------------------------------------------------------------------------------------------
 // Small batches (the reference's own shape is ONE env: train.py:33-43): one WARP per env.  With one env per thread a step
 // is a chain of ~10,000 dependent FMAs in a single thread (20 us per env step whatever the batch size below ~75k envs); here
-// the 64 hidden units of a layer are spread over the 32 lanes (units lane and lane + 32), the env state and the observation
+// the 64 hidden units of a layer are spread over the 32 lanes (units 2 * lane and 2 * lane + 1: one LDS.64 + one packed FMA per input), the env state and the observation
 // are replicated in every lane (the env step is computed redundantly: no broadcast, no divergence), the activations of a
 // layer go through 256 bytes of shared memory per warp.  Same float32 arithmetic and the same fmaf order per hidden unit as
 // policy_rollout_kernel (layers 1 and 2 are bit-identical); the four / one head sums are warp reductions.
@@ -281,34 +277,39 @@ constexpr size_t kPolicySmallSmem = sizeof(MlpSmem) + sizeof(float) * kSmallWarp
 template <int NOUT>
 __device__ __forceinline__ void tower_forward_warp(const MlpSmem& S, float* __restrict__ hbuf, const int t, const float (&x)[kObs],
                                                    float (&out)[NOUT], const int lane) {
-  float a0 = S.b1[t][lane], a1 = S.b1[t][lane + 32];
+  // this lane's two hidden units are 2 * lane and 2 * lane + 1: one LDS.64 of weights + one packed FMA per input
+  const int u = 2 * lane;
+  float2 a = *reinterpret_cast<const float2*>(S.b1[t] + u);
 #pragma unroll
   for (int i = 0; i < kObs; ++i) {
-    a0 = fmaf(S.W1T[t][i][lane], x[i], a0);
-    a1 = fmaf(S.W1T[t][i][lane + 32], x[i], a1);
+    const float2 w = *reinterpret_cast<const float2*>(S.W1T[t][i] + u);
+    fma2(a.x, a.y, w.x, w.y, x[i], x[i]);
   }
-  a0 = tanh_fast(a0); a1 = tanh_fast(a1);
+  a.x = tanh_fast(a.x); a.y = tanh_fast(a.y);
   __syncwarp();                                 // the previous tower's readers of hbuf are done
-  hbuf[lane] = a0; hbuf[lane + 32] = a1;
+  *reinterpret_cast<float2*>(hbuf + u) = a;
   __syncwarp();
-  float c0 = S.b2[t][lane], c1 = S.b2[t][lane + 32];
+  float2 c = *reinterpret_cast<const float2*>(S.b2[t] + u);
 #pragma unroll
   for (int k4 = 0; k4 < kHid / 4; ++k4) {
     const float4 h = reinterpret_cast<const float4*>(hbuf)[k4];          // warp-broadcast
-    c0 = fmaf(S.W2T[t][4 * k4][lane], h.x, c0);          c1 = fmaf(S.W2T[t][4 * k4][lane + 32], h.x, c1);
-    c0 = fmaf(S.W2T[t][4 * k4 + 1][lane], h.y, c0);      c1 = fmaf(S.W2T[t][4 * k4 + 1][lane + 32], h.y, c1);
-    c0 = fmaf(S.W2T[t][4 * k4 + 2][lane], h.z, c0);      c1 = fmaf(S.W2T[t][4 * k4 + 2][lane + 32], h.z, c1);
-    c0 = fmaf(S.W2T[t][4 * k4 + 3][lane], h.w, c0);      c1 = fmaf(S.W2T[t][4 * k4 + 3][lane + 32], h.w, c1);
+    const float2 w0 = *reinterpret_cast<const float2*>(S.W2T[t][4 * k4] + u), w1 = *reinterpret_cast<const float2*>(S.W2T[t][4 * k4 + 1] + u);
+    const float2 w2 = *reinterpret_cast<const float2*>(S.W2T[t][4 * k4 + 2] + u), w3 = *reinterpret_cast<const float2*>(S.W2T[t][4 * k4 + 3] + u);
+    fma2(c.x, c.y, w0.x, w0.y, h.x, h.x);
+    fma2(c.x, c.y, w1.x, w1.y, h.y, h.y);
+    fma2(c.x, c.y, w2.x, w2.y, h.z, h.z);
+    fma2(c.x, c.y, w3.x, w3.y, h.w, h.w);
   }
-  c0 = tanh_fast(c0); c1 = tanh_fast(c1);
+  const float c0 = tanh_fast(c.x), c1 = tanh_fast(c.y);
   if constexpr (NOUT == kAct) {
-    const float4 w0 = reinterpret_cast<const float4*>(S.W3piT[lane])[0], w1 = reinterpret_cast<const float4*>(S.W3piT[lane + 32])[0];
+    const float4 w0 = reinterpret_cast<const float4*>(S.W3piT[u])[0], w1 = reinterpret_cast<const float4*>(S.W3piT[u + 1])[0];
     out[0] = warp_sum(fmaf(w1.x, c1, w0.x * c0)) + S.b3pi[0];
     out[1] = warp_sum(fmaf(w1.y, c1, w0.y * c0)) + S.b3pi[1];
     out[2] = warp_sum(fmaf(w1.z, c1, w0.z * c0)) + S.b3pi[2];
     out[3] = warp_sum(fmaf(w1.w, c1, w0.w * c0)) + S.b3pi[3];
   } else {
-    out[0] = warp_sum(fmaf(S.W3vf[lane + 32], c1, S.W3vf[lane] * c0)) + S.b3vf;
+    const float2 w = *reinterpret_cast<const float2*>(S.W3vf + u);
+    out[0] = warp_sum(fmaf(w.y, c1, w.x * c0)) + S.b3vf;
   }
 }
 

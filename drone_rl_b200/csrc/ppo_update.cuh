@@ -66,8 +66,7 @@ __device__ __forceinline__ void tower_forward_keep(const MlpSmem& S, const int t
 #pragma unroll
     for (int q = 0; q < kHid / 4; ++q) {
       const float4 w = reinterpret_cast<const float4*>(S.W1T[t][i])[q];
-      h1[4 * q] = fmaf(w.x, xi, h1[4 * q]); h1[4 * q + 1] = fmaf(w.y, xi, h1[4 * q + 1]);
-      h1[4 * q + 2] = fmaf(w.z, xi, h1[4 * q + 2]); h1[4 * q + 3] = fmaf(w.w, xi, h1[4 * q + 3]);
+      fma4s(h1 + 4 * q, w, xi);
     }
   }
 #pragma unroll
@@ -97,8 +96,7 @@ __device__ __forceinline__ void tower_forward_keep(const MlpSmem& S, const int t
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const float4 w = reinterpret_cast<const float4*>(S.W2T[t][i] + 16 * c)[q];
-        acc[4 * q] = fmaf(w.x, hi, acc[4 * q]); acc[4 * q + 1] = fmaf(w.y, hi, acc[4 * q + 1]);
-        acc[4 * q + 2] = fmaf(w.z, hi, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(w.w, hi, acc[4 * q + 3]);
+        fma4s(acc + 4 * q, w, hi);
       }
     }
 #pragma unroll
@@ -113,8 +111,7 @@ __device__ __forceinline__ void tower_forward_keep(const MlpSmem& S, const int t
         const int j = 16 * c + 4 * q + e;
         if constexpr (NOUT == kAct) {
           const float4 w = reinterpret_cast<const float4*>(S.W3piT[j])[0];
-          out[0] = fmaf(w.x, a4[e], out[0]); out[1] = fmaf(w.y, a4[e], out[1]);
-          out[2] = fmaf(w.z, a4[e], out[2]); out[3] = fmaf(w.w, a4[e], out[3]);
+          fma4s(out, w, a4[e]);
         } else {
           out[0] = fmaf(S.W3vf[j], a4[e], out[0]);
         }
@@ -150,8 +147,7 @@ __device__ __forceinline__ void tower_backward(const UpdSmem& U, const int t, co
 #pragma unroll
       for (int qq = 0; qq < kHid / 4; ++qq) {
         const float4 w = reinterpret_cast<const float4*>(U.W2[t][j])[qq];
-        d1[4 * qq] = fmaf(w.x, dj, d1[4 * qq]); d1[4 * qq + 1] = fmaf(w.y, dj, d1[4 * qq + 1]);
-        d1[4 * qq + 2] = fmaf(w.z, dj, d1[4 * qq + 2]); d1[4 * qq + 3] = fmaf(w.w, dj, d1[4 * qq + 3]);
+        fma4s(d1 + 4 * qq, w, dj);
       }
     }
     reinterpret_cast<float4*>(rowB)[q] = make_float4(d4[0], d4[1], d4[2], d4[3]);
@@ -182,7 +178,7 @@ __device__ __forceinline__ void wgrad_hidden(UpdSmem& U, int w2off, int b2off, i
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
-      for (int b = 0; b < 8; ++b) acc[a][b] = fmaf(dd[a], hh[b], acc[a][b]);
+      for (int b = 0; b < 8; b += 2) fma2(acc[a][b], acc[a][b + 1], hh[b], hh[b + 1], dd[a], dd[a]);
   }
 #pragma unroll
   for (int a = 0; a < 4; ++a)
@@ -205,10 +201,8 @@ __device__ __forceinline__ void wgrad_input(UpdSmem& U, int w1off, int b1off, in
   for (int s = 0; s < rows; ++s) {
     const float2 d = reinterpret_cast<const float2*>(U.bufA[s])[jt];
     const float4 x = reinterpret_cast<const float4*>(U.bufX[s])[it];
-    acc[0][0] = fmaf(d.x, x.x, acc[0][0]); acc[0][1] = fmaf(d.x, x.y, acc[0][1]);
-    acc[0][2] = fmaf(d.x, x.z, acc[0][2]); acc[0][3] = fmaf(d.x, x.w, acc[0][3]);
-    acc[1][0] = fmaf(d.y, x.x, acc[1][0]); acc[1][1] = fmaf(d.y, x.y, acc[1][1]);
-    acc[1][2] = fmaf(d.y, x.z, acc[1][2]); acc[1][3] = fmaf(d.y, x.w, acc[1][3]);
+    fma4s(acc[0], x, d.x);
+    fma4s(acc[1], x, d.y);
   }
 #pragma unroll
   for (int a = 0; a < 2; ++a)

@@ -113,6 +113,20 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 __device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
 
+// A/B knobs of the elementwise phases (r02, profiles/README.md)
+#ifndef DRONECU_STASH_GROUPS
+#define DRONECU_STASH_GROUPS 1      // tanh' stash in the [chunk][sample][16 B] layout of bufA instead of swizzled 128-byte rows
+#endif
+#ifndef DRONECU_S5_BF16MUL
+#define DRONECU_S5_BF16MUL 0        // dZ1 = bf16(dH1) * stash as one HMUL2.BF16 per pair (two roundings) instead of fp32 products
+#endif
+__device__ __forceinline__ uint32_t mul_bf16x2(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+
+
 __device__ __forceinline__ void setup3(Smem3& S, const float* __restrict__ theta, const int tw) {
   const int tid = threadIdx.x;
   const int oW1 = tw ? O_VF_W1 : O_PI_W1, oB1 = tw ? O_VF_B1 : O_PI_B1, oW2 = tw ? O_VF_W2 : O_PI_W2;
@@ -322,8 +336,14 @@ __global__ void __launch_bounds__(tcb::kThreads3, 1) ppo_grad_bf16_kernel(const 
     // warpgroup still read in their dZ1 phase: with the private steps issued by warp 0 that aliasing produced one garbage
     // 8-feature block of dW1 per ~1500 launches at the c5 size (scratch/stress_determinism.py).
     unsigned char* const XS = S.bufB[wg];
+#if DRONECU_STASH_GROUPS
+    unsigned char* const rowG1 = S.XG[wg] + r * 16;        // chunk c of this sample at c * kGrp (the layout of bufA: conflict-free, immediate offsets)
+#define STASH_OFF(c) ((c) * kGrp)
+#else
     unsigned char* const rowG1 = S.XG[wg] + r * 128;       // 8 chunks of 16 B, chunk c at ((c ^ (r & 7)) << 4)
     const int sw = r & 7;
+#define STASH_OFF(c) (((c) ^ sw) << 4)
+#endif
     unsigned long long* const full = &S.full[wg];
     unsigned long long* const fullA = &S.fullA[wg];
     unsigned long long* const done = &S.done[wg];
@@ -463,9 +483,11 @@ __global__ void __launch_bounds__(tcb::kThreads3, 1) ppo_grad_bf16_kernel(const 
             const float* h = v + 8 * j;
             *reinterpret_cast<uint4*>(rowA + (2 * c + j) * kGrp) =
                 make_uint4(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]), pack_bf16(h[4], h[5]), pack_bf16(h[6], h[7]));
-            *reinterpret_cast<uint4*>(rowG1 + (((2 * c + j) ^ sw) << 4)) =
-                make_uint4(pack_bf16(fmaf(-h[0], h[0], 1.f), fmaf(-h[1], h[1], 1.f)), pack_bf16(fmaf(-h[2], h[2], 1.f), fmaf(-h[3], h[3], 1.f)),
-                           pack_bf16(fmaf(-h[4], h[4], 1.f), fmaf(-h[5], h[5], 1.f)), pack_bf16(fmaf(-h[6], h[6], 1.f), fmaf(-h[7], h[7], 1.f)));
+            float t[8];
+#pragma unroll
+            for (int i = 0; i < 8; i += 2) one_minus_sq2(h[i], h[i + 1], t[i], t[i + 1]);
+            *reinterpret_cast<uint4*>(rowG1 + STASH_OFF(2 * c + j)) =
+                make_uint4(pack_bf16(t[0], t[1]), pack_bf16(t[2], t[3]), pack_bf16(t[4], t[5]), pack_bf16(t[6], t[7]));
           }
 #if DRONECU_TF32_ROUND
 #pragma unroll
@@ -502,7 +524,8 @@ __global__ void __launch_bounds__(tcb::kThreads3, 1) ppo_grad_bf16_kernel(const 
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const float4 b = reinterpret_cast<const float4*>(S.b2 + 16 * c)[q];
-            v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
+            add2(v[4 * q], v[4 * q + 1], b.x, b.y);
+            add2(v[4 * q + 2], v[4 * q + 3], b.z, b.w);
           }
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = tanh_mufu(v[i]);
@@ -596,7 +619,11 @@ __global__ void __launch_bounds__(tcb::kThreads3, 1) ppo_grad_bf16_kernel(const 
         ld_fence(d);
         ld_fence(h);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) d[i] = d[i] * fmaf(-h[i], h[i], 1.0f);
+        for (int i = 0; i < 16; i += 2) {
+          float t0, t1;
+          one_minus_sq2(h[i], h[i + 1], t0, t1);
+          mul2(d[i], d[i + 1], t0, t1);
+        }
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           const float* z = d + 8 * j;
@@ -620,7 +647,7 @@ __global__ void __launch_bounds__(tcb::kThreads3, 1) ppo_grad_bf16_kernel(const 
       {
         uint4 g1[8];                              // the stash does not depend on S5: read it while S5 runs
 #pragma unroll
-        for (int c = 0; c < 8; ++c) g1[c] = *reinterpret_cast<const uint4*>(rowG1 + ((c ^ sw) << 4));
+        for (int c = 0; c < 8; ++c) g1[c] = *reinterpret_cast<const uint4*>(rowG1 + STASH_OFF(c));
         mbar_wait(doneA, phA); phA ^= 1; fence_after();
         TSTAMP(tlog, it, 12);
         float va[16], vb[16];
@@ -634,10 +661,19 @@ __global__ void __launch_bounds__(tcb::kThreads3, 1) ppo_grad_bf16_kernel(const 
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
             const uint4 g = g1[2 * c + j];
-            const float* z = v + 8 * j;
+            float* z = v + 8 * j;
+#if DRONECU_S5_BF16MUL
             *reinterpret_cast<uint4*>(rowA + (2 * c + j) * kGrp) =
-                make_uint4(pack_bf16(z[0] * bf16_lo(g.x), z[1] * bf16_hi(g.x)), pack_bf16(z[2] * bf16_lo(g.y), z[3] * bf16_hi(g.y)),
-                           pack_bf16(z[4] * bf16_lo(g.z), z[5] * bf16_hi(g.z)), pack_bf16(z[6] * bf16_lo(g.w), z[7] * bf16_hi(g.w)));
+                make_uint4(mul_bf16x2(pack_bf16(z[0], z[1]), g.x), mul_bf16x2(pack_bf16(z[2], z[3]), g.y),
+                           mul_bf16x2(pack_bf16(z[4], z[5]), g.z), mul_bf16x2(pack_bf16(z[6], z[7]), g.w));
+            continue;
+#endif
+            mul2(z[0], z[1], bf16_lo(g.x), bf16_hi(g.x));
+            mul2(z[2], z[3], bf16_lo(g.y), bf16_hi(g.y));
+            mul2(z[4], z[5], bf16_lo(g.z), bf16_hi(g.z));
+            mul2(z[6], z[7], bf16_lo(g.w), bf16_hi(g.w));
+            *reinterpret_cast<uint4*>(rowA + (2 * c + j) * kGrp) =
+                make_uint4(pack_bf16(z[0], z[1]), pack_bf16(z[2], z[3]), pack_bf16(z[4], z[5]), pack_bf16(z[6], z[7]));
           }
           if (c < 3) ld_fence(w);
         }

@@ -256,7 +256,8 @@ __device__ __forceinline__ void tower(Smem& S, const int t, const float (&xv)[16
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const float4 b = reinterpret_cast<const float4*>(S.b2[t] + 16 * c)[q];
-      v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
+      add2(v[4 * q], v[4 * q + 1], b.x, b.y);
+      add2(v[4 * q + 2], v[4 * q + 3], b.z, b.w);
     }
     if (dbg2) {
 #pragma unroll
@@ -266,9 +267,7 @@ __device__ __forceinline__ void tower(Smem& S, const int t, const float (&xv)[16
     for (int i = 0; i < 16; ++i) {
       const float a = tanh_mufu(v[i]);
       if constexpr (NOUT == kAct) {
-        const float4 w = reinterpret_cast<const float4*>(S.W3piT[16 * c + i])[0];
-        out[0] = fmaf(w.x, a, out[0]); out[1] = fmaf(w.y, a, out[1]);
-        out[2] = fmaf(w.z, a, out[2]); out[3] = fmaf(w.w, a, out[3]);
+        fma4s(out, reinterpret_cast<const float4*>(S.W3piT[16 * c + i])[0], a);
       } else {
         out[0] = fmaf(S.W3vf[16 * c + i], a, out[0]);
       }
