@@ -489,7 +489,8 @@ __global__ void __launch_bounds__(tcu::kThreads, 1) ppo_grad_tc_kernel(const __g
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const float4 b = reinterpret_cast<const float4*>(S.b2 + 16 * c)[q];
-            v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
+            add2(v[4 * q], v[4 * q + 1], b.x, b.y);
+            add2(v[4 * q + 2], v[4 * q + 3], b.z, b.w);
           }
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = to_tf32_fast(tanh_mufu(v[i]));
@@ -572,7 +573,12 @@ __global__ void __launch_bounds__(tcu::kThreads, 1) ppo_grad_tc_kernel(const __g
           float (&w)[16] = (c & 1) ? da : db;
           if (c < 3) ld16_issue(tL + kColP + 16 * (c + 1), w);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) d[i] = to_tf32_fast(d[i] * fmaf(-h[c][i], h[c][i], 1.0f));
+          for (int i = 0; i < 16; i += 2) {
+            float t0, t1;
+            one_minus_sq2(h[c][i], h[c][i + 1], t0, t1);
+            mul2(d[i], d[i + 1], t0, t1);
+            d[i] = to_tf32_fast(d[i]); d[i + 1] = to_tf32_fast(d[i + 1]);
+          }
           st16(tL + kColQ + 16 * c, d);
 #pragma unroll
           for (int q = 0; q < 4; ++q) *mn_quad(bufB, r, 4 * c + q) = make_float4(d[4 * q], d[4 * q + 1], d[4 * q + 2], d[4 * q + 3]);
@@ -601,9 +607,13 @@ __global__ void __launch_bounds__(tcu::kThreads, 1) ppo_grad_tc_kernel(const __g
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const float4 h = h1[4 * c + q];
+            float t0, t1, t2, t3;
+            one_minus_sq2(h.x, h.y, t0, t1);
+            one_minus_sq2(h.z, h.w, t2, t3);
+            mul2(v[4 * q], v[4 * q + 1], t0, t1);
+            mul2(v[4 * q + 2], v[4 * q + 3], t2, t3);
             *mn_quad(bufA, r, 4 * c + q) =
-                make_float4(to_tf32_fast(v[4 * q] * fmaf(-h.x, h.x, 1.0f)), to_tf32_fast(v[4 * q + 1] * fmaf(-h.y, h.y, 1.0f)),
-                            to_tf32_fast(v[4 * q + 2] * fmaf(-h.z, h.z, 1.0f)), to_tf32_fast(v[4 * q + 3] * fmaf(-h.w, h.w, 1.0f)));
+                make_float4(to_tf32_fast(v[4 * q]), to_tf32_fast(v[4 * q + 1]), to_tf32_fast(v[4 * q + 2]), to_tf32_fast(v[4 * q + 3]));
           }
           if (c < 3) ld_fence(w);
         }

@@ -249,6 +249,7 @@ __device__ __forceinline__ void tower(Smem& S, const int t, const float (&xv)[16
   } else {
     out[0] = S.b3vf;
   }
+  float odd = 0.f;
 #pragma unroll
   for (int c = 0; c < kN2 / 16; ++c) {
     float v[16];
@@ -263,16 +264,19 @@ __device__ __forceinline__ void tower(Smem& S, const int t, const float (&xv)[16
 #pragma unroll
       for (int i = 0; i < 16; ++i) dbg2[16 * c + i] = v[i];
     }
+    if constexpr (NOUT == kAct) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const float a = tanh_mufu(v[i]);
-      if constexpr (NOUT == kAct) {
-        fma4s(out, reinterpret_cast<const float4*>(S.W3piT[16 * c + i])[0], a);
-      } else {
-        out[0] = fmaf(S.W3vf[16 * c + i], a, out[0]);
+      for (int i = 0; i < 16; ++i) fma4s(out, reinterpret_cast<const float4*>(S.W3piT[16 * c + i])[0], tanh_mufu(v[i]));
+    } else {                    // one output: even / odd hidden units in the two halves of a packed accumulator
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 w = reinterpret_cast<const float4*>(S.W3vf + 16 * c)[q];
+        fma2(out[0], odd, w.x, w.y, tanh_mufu(v[4 * q]), tanh_mufu(v[4 * q + 1]));
+        fma2(out[0], odd, w.z, w.w, tanh_mufu(v[4 * q + 2]), tanh_mufu(v[4 * q + 3]));
       }
     }
   }
+  if constexpr (NOUT != kAct) out[0] += odd;
   // the next tower's X store aliases D2: a thread only ever touches its own lane, and the MMA that
   // wrote D2 has completed (mbarrier), so no further barrier is needed here.
 }

@@ -14,7 +14,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 lib = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "drone_rl_b200", "libdronecu.so")
 WATCH = ["UTCHMMA", "UTCQMMA", "UTCMMA", "LDTM", "STTM", "UTCBAR", "UTCATOMSWS", "UTMALDG", "UTMASTG", "UBLKCP", "SYNCS", "MUFU.TANH",
-         "MUFU.EX2", "MUFU.RCP", "HMMA", "FFMA", "STG.E.128", "LDG.E.128", "ST.E.STRONG.SYS", "LD.E.STRONG.SYS", "MEMBAR.SC.SYS", "MEMBAR.ALL.SYS"]
+         "MUFU.EX2", "MUFU.RCP", "HMMA", "FFMA", "FFMA2", "FMUL2", "FADD2", "STG.E.128", "LDG.E.128", "ST.E.STRONG.SYS", "LD.E.STRONG.SYS", "MEMBAR.SC.SYS", "MEMBAR.ALL.SYS"]
 out = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True, check=True).stdout
 kern, counts, total = None, collections.OrderedDict(), collections.Counter()
 for line in out.splitlines():
@@ -29,7 +29,7 @@ for line in out.splitlines():
         op = m.group(1)
         total[kern] += 1
         for w in WATCH:
-            if op == w or op.startswith(w + ".") or (w.count(".") and op.startswith(w)):
+            if op == w or op.startswith(w + ".") or (w.count(".") and op.startswith(w)):      # FFMA does not count FFMA2
                 counts[kern][w] += 1
 print(f"# {os.path.relpath(lib, ROOT)}: SASS opcode counts per kernel (cuobjdump -sass, sm_100a)")
 print(f"# {'kernel':<58} {'instrs':>7}  " + " ".join(f"{w}" for w in WATCH))

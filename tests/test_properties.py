@@ -4,9 +4,11 @@ CPU half (``-m "not gpu"``): the float64 oracle against the LIVE unmodified refe
 container's /root/reference or the staged oracle/_ref archive) on generated states -- finite, huge, sub-normal, inf, NaN:
 bit-identical next state / reward / done for the vectorized env, NaN never terminates (drone.py:154), the time limit takes
 precedence (drone.py:156-157), 0 * inf = NaN in the body-rate / Euler-rate terms (drone.py:138, :181-186).
-GPU half: one teacher-forced CUDA step from generated float32 states against the oracle: identical NaN / inf pattern,
+GPU half: one teacher-forced CUDA step from generated float32 states against the oracle: a NaN only where the other side is non-finite,
 identical done bits away from the thresholds, values within 1e-5 * max(|ref|, 1, term magnitudes).
 """
+import os
+
 import numpy as np
 import pytest
 from hypothesis import HealthCheck, given, settings
@@ -17,6 +19,10 @@ from oracle import drone_oracle as do
 from oracle import ref_import, verify
 
 np.seterr(all="ignore")
+
+# The suite the driver runs must be reproducible: the examples are derived from the test itself (derandomize).  Exploration:
+# DRONECU_HYPOTHESIS_RANDOM=1 python -m pytest tests/test_properties.py --hypothesis-seed=N   (how the 0 * inf case below was found)
+_DERANDOMIZE = os.environ.get("DRONECU_HYPOTHESIS_RANDOM") is None
 
 finite32 = st.floats(min_value=-1e6, max_value=1e6, allow_nan=False, allow_infinity=False, width=32)
 wild32 = st.one_of(finite32, st.floats(width=32, allow_nan=True, allow_infinity=True),
@@ -29,7 +35,7 @@ def _states(n, elements):
 
 
 @pytest.mark.skipif(not ref_import.available(), reason="the reference is not present (neither /root/reference nor oracle/_ref)")
-@settings(max_examples=60, deadline=None, suppress_health_check=list(HealthCheck))
+@settings(max_examples=60, deadline=None, derandomize=_DERANDOMIZE, suppress_health_check=list(HealthCheck))
 @given(_states(8, wild32))
 def test_oracle_equals_live_reference_on_wild_states(s):
     pos, vel, eul, om, act = s
@@ -46,7 +52,7 @@ def test_oracle_equals_live_reference_on_wild_states(s):
 
 
 @pytest.mark.skipif(not ref_import.available(), reason="the reference is not present")
-@settings(max_examples=40, deadline=None, suppress_health_check=list(HealthCheck))
+@settings(max_examples=40, deadline=None, derandomize=_DERANDOMIZE, suppress_health_check=list(HealthCheck))
 @given(hnp.arrays(np.float32, (3,), elements=wild32), hnp.arrays(np.float32, (3,), elements=wild32),
        st.integers(min_value=0, max_value=199))
 def test_single_env_time_limit_takes_precedence_and_nan_never_crashes(pos, om, step):
@@ -79,7 +85,7 @@ def test_single_env_time_limit_takes_precedence_and_nan_never_crashes(pos, om, s
 
 
 @pytest.mark.gpu
-@settings(max_examples=60, deadline=None, suppress_health_check=list(HealthCheck))
+@settings(max_examples=60, deadline=None, derandomize=_DERANDOMIZE, suppress_health_check=list(HealthCheck))
 @given(_states(64, wild32), st.sampled_from(["single", "vector"]))
 def test_gpu_step_matches_oracle_on_wild_states(s, which):
     torch = pytest.importorskip("torch")
@@ -107,7 +113,11 @@ def test_gpu_step_matches_oracle_on_wild_states(s, which):
     g = got["obs"].astype(np.float64)
     # float32 overflow: the oracle's float64 value may be finite where |value| exceeds the float32 range -> compare after the cast
     ref32 = ref.astype(np.float32).astype(np.float64)
-    assert np.array_equal(np.isnan(g), np.isnan(ref32)), "NaN pattern"
+    # NaN pattern: a NaN on one side needs a non-finite value on the other.  Not "NaN on both": with infinite inputs the two
+    # sides may disagree between inf and NaN, e.g. omega = inf, phi = theta = 4e-24: the Euler-rate term (sin phi tan theta) q
+    # is 1.6e-47 * inf = inf in the reference's float64 but 0 * inf = NaN in float32, where the product underflows.
+    assert not (np.isnan(g) & np.isfinite(ref32)).any(), "NaN where the reference is finite"
+    assert not (np.isnan(ref32) & np.isfinite(g)).any(), "finite where the reference is NaN"
     # values: the checker's tolerance (term magnitudes), on entries that are finite on both sides and not at the float32 edge
     sphi, cphi, cosp, tanp = np.sin(e64[:, 0]), np.cos(e64[:, 0]), np.cos(e64[:, 1]), np.tan(e64[:, 1])
     mix = np.abs(o64[:, 1] * sphi) + np.abs(o64[:, 2] * cphi)
