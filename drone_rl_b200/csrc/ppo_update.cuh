@@ -523,7 +523,9 @@ struct PermKey {
 
 __host__ __device__ inline uint32_t perm_apply(uint32_t x, const PermKey& K, uint32_t n) {
   do {
+#ifdef __CUDA_ARCH__
 #pragma unroll
+#endif
     for (int r = 0; r < 4; ++r) {
       x ^= x >> K.shift;
       x = (x * K.mul[r] + K.add[r]) & K.mask;

@@ -45,7 +45,7 @@
 #if DRONECU_TC_TIMING
 #define TSTAMP(buf, it, k) do { if ((buf) != nullptr && (it) < 16) (buf)[(it) * 16 + (k)] = clock64(); } while (0)
 #else
-#define TSTAMP(buf, it, k) do { } while (0)
+#define TSTAMP(buf, it, k) do { (void)(buf); } while (0)
 #endif
 
 namespace dronecu {
@@ -418,6 +418,7 @@ __global__ void __launch_bounds__(tcu::kThreads, 1) ppo_grad_tc_kernel(const __g
 #if DRONECU_TC_TIMING
     if (A.dbg != nullptr && blockIdx.x == 0 && tw == 0 && wg == 0 && r == 0) tlog = reinterpret_cast<long long*>(A.dbg);
 #endif
+    (void)tlog;
     int64_t tile = (int64_t)blockIdx.x * kWG + wg;
     int row_cur = row_of(tile), row_nxt = row_of(tile + stride);
     RowIn cur;

@@ -396,8 +396,10 @@ __global__ void __launch_bounds__(tcb::kThreads3, 1) ppo_grad_bf16_kernel(const 
     unsigned long long* const fullA = &S.fullA[wg];
     unsigned long long* const done = &S.done[wg];
     unsigned long long* const doneA = &S.doneA[wg];
+#if DRONECU_S5_SPLIT
     unsigned long long* const doneW = &S.doneW[wg];
     uint32_t phW = 0;
+#endif
     uint32_t phA = 0;
 #if !DRONECU_PRIVATE_ISSUER_WARPS
     uint32_t phf = 0;
