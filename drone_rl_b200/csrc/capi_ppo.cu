@@ -500,7 +500,6 @@ extern "C" int dronecu_ppo_dp_connect(dronecu_ppo* p, int world, const void* ipc
       p->dp_opened[r] = true;
     }
   }
-  CUDA_TRY(cudaFuncSetAttribute(ppo_apply_dp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * kGradLen)));
   p->dp.world = world;
   return DRONECU_OK;
 }
@@ -545,7 +544,7 @@ extern "C" int dronecu_ppo_apply_dp(dronecu_ppo* p, float* d_params, float* d_gr
   a.step = p->d_step;
   a.beta1 = p->cfg.beta1; a.beta2 = p->cfg.beta2; a.eps = p->cfg.adam_eps; a.max_norm = p->cfg.max_grad_norm;
   a.info = d_info; a.info_sum = p->info_sum;
-  ppo_apply_dp_kernel<<<1, kDpBlock, sizeof(float) * kGradLen, (cudaStream_t)stream>>>(p->dp, a, d_grad);
+  ppo_apply_dp_kernel<<<1, kDpBlock, 0, (cudaStream_t)stream>>>(p->dp, a, d_grad);
   p->launches += 1;
   CUDA_TRY(cudaGetLastError());
   return DRONECU_OK;

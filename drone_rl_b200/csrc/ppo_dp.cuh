@@ -114,52 +114,28 @@ __global__ void __launch_bounds__(kDpBlock) dp_allreduce_f64_kernel(const __grid
 // exchange + clip_grad_norm_ + Adam.  A.grad: the LOCAL sum-form gradient (kGradLen floats: output of ppo_reduce_*), replaced
 // by the sum over the ranks; A.inv_count is ignored: the denominator is the summed sample count grad[kParams + 4].
 __global__ void __launch_bounds__(kDpBlock) ppo_apply_dp_kernel(const __grid_constant__ DpArgs D, const AdamArgs A, float* __restrict__ grad_io) {
-  extern __shared__ float g_s[];                 // [kGradLen] summed gradient + statistics
   __shared__ float red[32];
-  __shared__ float coef_s, lr_over_bc1_s, inv_sqrt_bc2_s;
+  __shared__ float scal[3];
+  __shared__ float stats_s[kGradLen - kParams];  // the summed statistics (sample count at [4])
+  static_assert(kDpBlock == kApplyBlock, "one thread layout for both apply kernels");
   const uint32_t s = (uint32_t)(*D.seq + 1ull);
   dp_exchange(D, grad_io, kGradLen, s);
   const int parity = (int)(s & 1u);
-  for (int i = threadIdx.x; i < kGradLen; i += kDpBlock) {
-    float acc = __ldcg(dp_slot(D.mail[D.rank], D.world, parity, 0) + i);
-    for (int r = 1; r < D.world; ++r) acc += __ldcg(dp_slot(D.mail[D.rank], D.world, parity, r) + i);
-    g_s[i] = acc;
-    grad_io[i] = acc;
-  }
-  if (threadIdx.x == 0) {
-    AdamClock* clk = reinterpret_cast<AdamClock*>(A.step);
-    const double p1 = clk->b1pow * (double)A.beta1, p2 = clk->b2pow * (double)A.beta2;
-    clk->step += 1; clk->b1pow = p1; clk->b2pow = p2;
-    lr_over_bc1_s = (float)((double)A.lr / (1.0 - p1));
-    inv_sqrt_bc2_s = (float)(1.0 / sqrt(1.0 - p2));
-  }
-  __syncthreads();
-  const float inv_count = 1.0f / g_s[kParams + 4];
-  float sq = 0.f;
-  for (int i = threadIdx.x; i < kParams; i += kDpBlock) {
-    const float g = g_s[i] * inv_count;
-    sq = fmaf(g, g, sq);
-  }
-  sq = warp_sum(sq);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sq;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    float v = red[threadIdx.x];
-    v = warp_sum(v);
-    if (threadIdx.x == 0) coef_s = sqrtf(v);          // the pre-clip gradient norm
+  float g[kApplyPer];
+#pragma unroll
+  for (int k = 0; k < kApplyPer; ++k) {
+    const int i = threadIdx.x + k * kDpBlock;
+    float acc = 0.f;
+    if (i < kGradLen) {
+      acc = __ldcg(dp_slot(D.mail[D.rank], D.world, parity, 0) + i);
+      for (int r = 1; r < D.world; ++r) acc += __ldcg(dp_slot(D.mail[D.rank], D.world, parity, r) + i);
+      grad_io[i] = acc;
+      if (i >= kParams) stats_s[i - kParams] = acc;
+    }
+    g[k] = (i < kParams) ? acc : 0.f;
   }
   __syncthreads();
-  const float norm = coef_s;
-  apply_publish_info(A, g_s + kParams, inv_count, norm);
-  const float coef = fminf(A.max_norm / (norm + 1e-6f), 1.0f) * inv_count;
-  const float lr_over_bc1 = lr_over_bc1_s, inv_sqrt_bc2 = inv_sqrt_bc2_s;
-  for (int i = threadIdx.x; i < kParams; i += kDpBlock) {
-    const float g = g_s[i] * coef;
-    const float m = A.beta1 * A.m[i] + (1.0f - A.beta1) * g;
-    const float v = A.beta2 * A.v[i] + (1.0f - A.beta2) * g * g;
-    A.m[i] = m; A.v[i] = v;
-    A.theta[i] -= lr_over_bc1 * m / (sqrtf(v) * inv_sqrt_bc2 + A.eps);
-  }
+  clip_adam_apply(A, g, stats_s, 1.0f / stats_s[4], red, scal);
   if (threadIdx.x == 0) *D.seq = *D.seq + 1ull;
 }
 
