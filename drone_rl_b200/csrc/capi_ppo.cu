@@ -324,16 +324,18 @@ static int ppo_grad_impl(dronecu_ppo* p, const float* d_params, const float* d_o
   a.adv = d_adv; a.ret = d_returns; a.index = d_index; a.first = first; a.m = m;
   a.adv_mean = adv_mean; a.adv_inv_std = adv_inv_std; a.adv_stats = d_adv_stats;
   a.clip = p->cfg.clip_range; a.vf_coef = p->cfg.vf_coef; a.ent_coef = p->cfg.ent_coef;
-  a.partials = p->partials; a.dbg = tensor_cores ? p->dbg : nullptr;
+  a.partials = p->partials; a.direct = nullptr; a.dbg = tensor_cores ? p->dbg : nullptr;
   const int64_t tiles = (m + kUpdBlock - 1) / kUpdBlock;
   cudaStream_t st = (cudaStream_t)stream;
   if (mode == 2) {
     // grid (x, 2): blockIdx.y = tower; one CTA per SM, three 128-sample tiles in flight per CTA, one partial vector per CTA
     const unsigned gx = (unsigned)std::max<int64_t>(1, std::min<int64_t>((tiles + tcb::kWG3 - 1) / tcb::kWG3, p->n_sm / 2));
+    a.direct = (gx == 1) ? d_grad : nullptr;       // one partial vector per tower: the kernel writes the gradient itself
     if (obs_stride == 16) ppo_grad_bf16_kernel<true><<<dim3(gx, 2), tcb::kThreads3, kTc3Smem, st>>>(a);
     else ppo_grad_bf16_kernel<false><<<dim3(gx, 2), tcb::kThreads3, kTc3Smem, st>>>(a);
     CUDA_TRY(cudaGetLastError());
-    ppo_reduce_tc_kernel<<<(kGradLen + 255) / 256, 256, 0, st>>>(p->partials, (int)gx, d_grad);
+    if (gx > 1) ppo_reduce_tc_kernel<<<(kGradLen + 255) / 256, 256, 0, st>>>(p->partials, (int)gx, d_grad);
+    else p->launches -= 1;
   } else if (tensor_cores) {
     // grid (x, 2): blockIdx.y = tower; one CTA per SM, two 128-sample tiles in flight per CTA
     const unsigned gx = (unsigned)std::max<int64_t>(1, std::min<int64_t>((tiles + tcu::kWG - 1) / tcu::kWG, p->n_sm / 2));

@@ -47,6 +47,7 @@ struct UpdArgs {
   const double* adv_stats;       // nullable: [sum, sum of squares, count] -> overrides the two scalars
   float clip, vf_coef, ent_coef;
   float* partials;           // [gridDim.x, kGradLen]
+  float* direct;             // ppo_grad_bf16_kernel with ONE CTA per tower: the gradient vector itself (no reduce launch); else nullptr
   float* dbg;                // nullable (tensor-core kernel only): raw TMEM dump [2 gridDim.x, 128 lanes, 256 columns]
 };
 

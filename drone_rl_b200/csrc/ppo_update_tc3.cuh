@@ -760,7 +760,10 @@ __global__ void __launch_bounds__(tcb::kThreads3, 1) ppo_grad_bf16_kernel(const 
         for (int w = 0; w < kWG3; ++w) s += ((S.wsum[w][0][q] + S.wsum[w][1][q]) + S.wsum[w][2][q]) + S.wsum[w][3][q];
         return s;
       };
-      float* const outv = A.partials + ((size_t)tw * gridDim.x + blockIdx.x) * kGradLen;
+      // one CTA per tower (minibatches of up to 384 samples -- the reference's batch_size 64): the two towers own disjoint
+      // entries of the gradient vector and write it directly, which saves the reduce launch (3 us of a ~23 us optimiser step)
+      const bool direct = A.direct != nullptr;
+      float* const outv = direct ? A.direct : A.partials + ((size_t)tw * gridDim.x + blockIdx.x) * kGradLen;
       const int oW1 = tw ? O_VF_W1 : O_PI_W1, oB1 = tw ? O_VF_B1 : O_PI_B1, oW2 = tw ? O_VF_W2 : O_PI_W2;
       const int oB2 = tw ? O_VF_B2 : O_PI_B2, oW3 = tw ? O_VF_W3 : O_PI_W3, oB3 = tw ? O_VF_B3 : O_PI_B3;
       const int nB3 = tw ? 1 : kAct;
@@ -768,7 +771,7 @@ __global__ void __launch_bounds__(tcb::kThreads3, 1) ppo_grad_bf16_kernel(const 
       if (it == 0) {         // no tile in this CTA at all (warpgroup 0 owns the CTA's first tile)
         for (int idx = r; idx < oB3 + nB3 - oW1; idx += 128) outv[oW1 + idx] = 0.f;
         if (tw == 0 && r < kAct) outv[O_LOGSTD + r] = 0.f;
-        if (r < kStats) outv[kParams + r] = 0.f;
+        if (r < kStats && (!direct || ((r == 1 || r == 4) == (tw == 1)))) outv[kParams + r] = 0.f;
       } else {
         const int j = 16 * wq + lane;               // accumulator row held by lanes 0..15 of each subpartition
         const bool own = lane < 16;
@@ -804,10 +807,10 @@ __global__ void __launch_bounds__(tcb::kThreads3, 1) ppo_grad_bf16_kernel(const 
         }
         if (tw == 0) {
           if (r < kAct) { outv[O_LOGSTD + r] = scalar(r); outv[O_PI_B3 + r] = scalar(4 + r); }
-          if (r < kStats) outv[kParams + r] = (r == 0) ? scalar(8) : (r == 2) ? scalar(9) : (r == 3) ? scalar(10) : 0.f;
+          if (r < kStats && !(direct && (r == 1 || r == 4))) outv[kParams + r] = (r == 0) ? scalar(8) : (r == 2) ? scalar(9) : (r == 3) ? scalar(10) : 0.f;
         } else {
           if (r == 0) outv[O_VF_B3] = scalar(0);
-          if (r < kStats) outv[kParams + r] = (r == 1) ? scalar(1) : (r == 4) ? scalar(2) : 0.f;
+          if (r < kStats && (!direct || r == 1 || r == 4)) outv[kParams + r] = (r == 1) ? scalar(1) : (r == 4) ? scalar(2) : 0.f;
         }
       }
     }

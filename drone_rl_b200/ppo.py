@@ -301,7 +301,9 @@ class PPO:
             # every rank holds m samples of this minibatch (checked in _dp_setup)
             _lib.check(self.lib.dronecu_ppo_apply(self._h, _ptr(self.params), _ptr(self._grad),
                                                   1.0 / (m * self.world), _ptr(self._info), st), "dronecu_ppo_apply")
-        self.launches += 3
+        # gradient kernel, its fixed-order reduce, apply; the bf16 kernel writes the gradient itself when one CTA per tower covers
+        # the minibatch (up to 3 tiles of 128 samples: capi_ppo.cu), which saves the reduce launch
+        self.launches += 2 if (self.update_precision == "bf16" and m <= 384) else 3
         self.n_updates += 1
 
     def launch_grad(self, index: Optional[torch.Tensor], first: int, m: int, stats_ptr, grad: torch.Tensor,
