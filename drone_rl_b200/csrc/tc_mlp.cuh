@@ -60,6 +60,40 @@ __device__ __forceinline__ float tanh_mufu(float x) {
   return y;
 }
 
+// Experiment (profiles/README.md): the rollout kernel is bound by the MUFU pipe (256 tanh per env-step at
+// 16 / clk / SM), so a share of the activations can be evaluated on the FMA pipe instead: odd minimax polynomial
+// x q(x^2) of degree 17 on [-3.75, 3.75] (input clamped; max abs error 5.9e-4, the size of tanh.approx's own 2^-11), two
+// activations per packed instruction: 4 FMNMX + 10 FFMA2 / FMUL2 per pair.  DRONECU_TANH_POLY_PAIRS = pairs per 16-wide chunk
+// that take this route (0 = all MUFU).
+#ifndef DRONECU_TANH_POLY_PAIRS
+#define DRONECU_TANH_POLY_PAIRS 0
+#endif
+__device__ __forceinline__ void tanh_poly2(float& x0, float& x1) {
+  constexpr float L = 3.75f;
+  const float a = fminf(fmaxf(x0, -L), L), b = fminf(fmaxf(x1, -L), L);
+  float t0 = a, t1 = b;
+  mul2(t0, t1, a, b);
+  float q0 = 1.370740944e-08f, q1 = 1.370740944e-08f;
+  constexpr float c[8] = {9.968600950e-01f, -3.149698032e-01f, 1.002266090e-01f, -2.373800408e-02f, 3.820229060e-03f,
+                          -3.979489950e-04f, 2.547277998e-05f, -9.067762226e-07f};
+#pragma unroll
+  for (int k = 7; k >= 0; --k) {                 // q = q * t + c[k]
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(pk2(q0, q1)), "l"(pk2(t0, t1)), "l"(pk2(c[k], c[k])));
+    upk2(d, q0, q1);
+  }
+  mul2(q0, q1, a, b);
+  x0 = q0; x1 = q1;
+}
+// tanh of a 16-wide chunk in place: the first DRONECU_TANH_POLY_PAIRS pairs on the FMA pipe, the rest on MUFU
+__device__ __forceinline__ void tanh_chunk16(float (&v)[16]) {
+#pragma unroll
+  for (int i = 0; i < 16; i += 2) {
+    if (i < 2 * DRONECU_TANH_POLY_PAIRS) tanh_poly2(v[i], v[i + 1]);
+    else { v[i] = tanh_mufu(v[i]); v[i + 1] = tanh_mufu(v[i + 1]); }
+  }
+}
+
 // byte offset of element (n, k) of an [N x K] K-major operand in the canonical no-swizzle layout
 __device__ __forceinline__ int umma_off(int n, int k, int K) {
   return (((n >> 3) * (K >> 2) + (k >> 2)) << 5) + ((n & 7) << 2) + (k & 3);   // in floats
@@ -221,8 +255,9 @@ __device__ __forceinline__ void tower(Smem& S, const int t, const float (&xv)[16
 #pragma unroll
       for (int i = 0; i < 16; ++i) dbg1[16 * c + i] = v[i];
     }
+    tanh_chunk16(v);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = to_tf32_fast(tanh_mufu(v[i]));
+    for (int i = 0; i < 16; ++i) v[i] = to_tf32_fast(v[i]);
     tmem_st16(tbase + kColD1 + 16 * c, v);
   }
   wait_st();
@@ -264,15 +299,16 @@ __device__ __forceinline__ void tower(Smem& S, const int t, const float (&xv)[16
 #pragma unroll
       for (int i = 0; i < 16; ++i) dbg2[16 * c + i] = v[i];
     }
+    tanh_chunk16(v);
     if constexpr (NOUT == kAct) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) fma4s(out, reinterpret_cast<const float4*>(S.W3piT[16 * c + i])[0], tanh_mufu(v[i]));
+      for (int i = 0; i < 16; ++i) fma4s(out, reinterpret_cast<const float4*>(S.W3piT[16 * c + i])[0], v[i]);
     } else {                    // one output: even / odd hidden units in the two halves of a packed accumulator
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const float4 w = reinterpret_cast<const float4*>(S.W3vf + 16 * c)[q];
-        fma2(out[0], odd, w.x, w.y, tanh_mufu(v[4 * q]), tanh_mufu(v[4 * q + 1]));
-        fma2(out[0], odd, w.z, w.w, tanh_mufu(v[4 * q + 2]), tanh_mufu(v[4 * q + 3]));
+        fma2(out[0], odd, w.x, w.y, v[4 * q], v[4 * q + 1]);
+        fma2(out[0], odd, w.z, w.w, v[4 * q + 2], v[4 * q + 3]);
       }
     }
   }
