@@ -369,6 +369,7 @@ def test_epoch_advantage_statistics(drl):
     from drone_rl_b200.ppo import PPO
     model = PPO(drl.DroneBatch(96, drl.EnvConfig.single(), seed=2), n_steps=21, seed=2)
     B, bs = 96 * 21, 500                                   # 4 full minibatches + one of 16
+    torch.manual_seed(5)
     adv = torch.randn(B, device="cuda") * 3 + 0.5
     perm = torch.randperm(B, device="cuda").to(torch.int32)
     n_mb = (B + bs - 1) // bs
