@@ -141,6 +141,9 @@ __device__ __forceinline__ void reset_env(EnvState& s, const EnvParams& P, uint6
 // quadrant taken from the low mantissa bits of a magic-number rounding, and the Cephes single-precision
 // minimax polynomials on [-pi/4, pi/4] (< 1.5 ulp).  NaN arguments fall through the check (fmaxf drops
 // NaN) and propagate through the arithmetic.
+#ifndef DRONECU_SINCOS_COMPACT
+#define DRONECU_SINCOS_COMPACT 0      // 1: compact the huge (lane, angle) pairs over the warp (measured: c2 -17 %, c4 -5 %; profiles/README.md)
+#endif
 __device__ __forceinline__ void sincos_reduced(float x, float& s, float& c) {
   const float j = fmaf(x, 0.636619772367581343f, 12582912.0f);      // 1.5 * 2^23: round to nearest integer
   const uint32_t q = __float_as_uint(j);
@@ -162,9 +165,58 @@ __device__ __forceinline__ void sincos_reduced(float x, float& s, float& c) {
   c = __uint_as_float(__float_as_uint(c0) ^ (((q + 1u) << 30) & 0x80000000u));   // quadrants 1, 2: cos < 0
 }
 
+// EXPERIMENT, off (DRONECU_SINCOS_COMPACT): measured slower -- in configs[1] the drones of a warp tumble together, so most lanes
+// hold huge angles at the same time (nothing to compact), and the out-of-line call costs the common path registers.
+// The rare path of sincos3: at least one lane of the warp holds an angle that is huge (>= 105615), inf or NaN.  Only THOSE
+// angles need libm's Payne-Hanek reduction (~200 instructions each, executed by the whole warp whoever needs it): the
+// (lane, angle) pairs that need it are compacted over the warp -- one pair per lane -- so that one sincosf call serves up to 32
+// of them, instead of every affected lane walking through three calls one after the other.  The reference's vectorized env
+// never resets (vectorized_drone.py:135-216): by step 1000 of configs[1] most warps hold a drone that has spun that far, and the
+// three serial calls were ~60 % of all executed instructions there (profiles/r02_c2_chain_model.md).
+// Full warps only (every kernel calls step_env with all 32 lanes converged); results are those of sincosf on the same argument.
+static __device__ __noinline__ void sincos3_huge(const float a, const float b, const float g, const bool ha, const bool hb, const bool hg,
+                                          float& sa, float& ca, float& sb, float& cb, float& sg, float& cg) {
+  constexpr unsigned kFull = 0xffffffffu;
+  const unsigned lane = threadIdx.x & 31u, below = (1u << lane) - 1u;
+  const unsigned ma = __ballot_sync(kFull, ha), mb = __ballot_sync(kFull, hb), mg = __ballot_sync(kFull, hg);
+  const int na = __popc(ma), nb = __popc(mb), total = na + nb + __popc(mg);
+  const int ia = __popc(ma & below), ib = na + __popc(mb & below), ig = na + nb + __popc(mg & below);   // this lane's items
+  for (int base = 0; base < total; base += 32) {
+    const int item = base + (int)lane;
+    const bool mine = item < total;
+    const int which = item < na ? 0 : (item < na + nb ? 1 : 2);
+    const unsigned msk = which == 0 ? ma : (which == 1 ? mb : mg);
+    const int nth = item - (which == 0 ? 0 : (which == 1 ? na : na + nb));
+    const int src = mine ? (int)__fns(msk, 0u, nth + 1) : 0;
+    const float xa = __shfl_sync(kFull, a, src), xb = __shfl_sync(kFull, b, src), xg = __shfl_sync(kFull, g, src);
+    float sx = 0.f, cx = 0.f;
+    if (mine) sincosf(which == 0 ? xa : (which == 1 ? xb : xg), &sx, &cx);
+    const int pa = ia - base, pb = ib - base, pg = ig - base;
+    const float s_a = __shfl_sync(kFull, sx, pa & 31), c_a = __shfl_sync(kFull, cx, pa & 31);
+    const float s_b = __shfl_sync(kFull, sx, pb & 31), c_b = __shfl_sync(kFull, cx, pb & 31);
+    const float s_g = __shfl_sync(kFull, sx, pg & 31), c_g = __shfl_sync(kFull, cx, pg & 31);
+    if (ha && pa >= 0 && pa < 32) { sa = s_a; ca = c_a; }
+    if (hb && pb >= 0 && pb < 32) { sb = s_b; cb = c_b; }
+    if (hg && pg >= 0 && pg < 32) { sg = s_g; cg = c_g; }
+  }
+}
+
 __device__ __forceinline__ void sincos3(float a, float b, float g, float& sa, float& ca, float& sb, float& cb,
                                         float& sg, float& cg) {
-  if (fmaxf(fmaxf(fabsf(a), fabsf(b)), fabsf(g)) < 105615.0f) {
+  constexpr float kLim = 105615.0f;
+  const bool small = fmaxf(fmaxf(fabsf(a), fabsf(b)), fabsf(g)) < kLim;       // false for huge, inf and NaN arguments
+#if DRONECU_SINCOS_COMPACT
+  const unsigned am = __activemask();
+  if (am == 0xffffffffu) {
+    sincos_reduced(a, sa, ca);
+    sincos_reduced(b, sb, cb);
+    sincos_reduced(g, sg, cg);
+    if (__all_sync(0xffffffffu, small)) return;
+    sincos3_huge(a, b, g, !(fabsf(a) < kLim), !(fabsf(b) < kLim), !(fabsf(g) < kLim), sa, ca, sb, cb, sg, cg);
+    return;
+  }
+#endif
+  if (small) {
     sincos_reduced(a, sa, ca);
     sincos_reduced(b, sb, cb);
     sincos_reduced(g, sg, cg);
